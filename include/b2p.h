@@ -1,0 +1,181 @@
+/*
+ * b2p.h — C ABI of the B200-native baseband -> power kernel library (libb2p.so).
+ *
+ * This is the drop-in boundary for the hot path of paf-baseband2power: the
+ * work the reference planned for kernel.cu / baseband2power.cu and never wrote
+ * (kernel.cu:1-7 and baseband2power.cu:1-16 are #includes only; the stage's
+ * conf_t at baseband2power.cuh:18-23 is the one declaration that exists).  The
+ * reference declares no function-level interface for this path, so each entry
+ * point cites the reference artefact whose contract it implements.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  `stream`
+ * arguments are a cudaStream_t passed as void* (NULL = the context's own
+ * compute stream).  Every int-returning call returns 0 (EXIT_SUCCESS) or a
+ * non-zero B2P_E* code, mirroring the EXIT_SUCCESS/EXIT_FAILURE convention of
+ * init_diskdb/do_diskdb (diskdb.cuh:32-34); the message is kept per context
+ * (b2p_last_error).  A context is not thread-safe: one context per
+ * (GPU, group of beam streams), used from one host thread at a time.
+ *
+ * There is no CPU fallback: every compute entry point fails when no CUDA
+ * device is usable.
+ */
+#ifndef B2P_H
+#define B2P_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2P_VERSION "0.1.0"
+
+/* error codes */
+#define B2P_OK        0
+#define B2P_EINVAL    1 /* bad argument / unsupported geometry */
+#define B2P_ECUDA     2 /* a CUDA runtime call failed (message holds file:line) */
+#define B2P_ENOMEM    3
+#define B2P_ESTATE    4 /* call made in the wrong state */
+
+/* accumulation modes (BASELINE.json north_star: exact int64 mode + float mode) */
+#define B2P_MODE_EXACT 0 /* uint64 sums, result independent of order: bit-exact */
+#define B2P_MODE_FLOAT 1 /* fp32 detect + fp64 integrate, <= 1e-6 relative */
+
+/* fused-kernel variants */
+#define B2P_KERNEL_AUTO 0
+#define B2P_KERNEL_LDG  1 /* 128-bit coalesced streaming loads, register pipeline */
+#define B2P_KERNEL_TMA  2 /* cp.async.bulk + mbarrier multi-stage shared-memory ring */
+
+#define B2P_MAX_BEAMS 64
+
+typedef struct b2p_ctx b2p_ctx;
+
+/*
+ * Geometry defaults come from paf-baseband2power.conf: NCHK_NIC 48 (:5),
+ * NSAMP_DF 128 (:2), NCHAN 336 (:24) -> 7 channels per chunk; the payload of a
+ * data frame is nsamp_df*nch_per_chunk*8 = 7168 B (capture.h:28).
+ */
+typedef struct b2p_params {
+  int device_id;        /* conf_t.device_id, baseband2power.cuh:20 (-d flag) */
+  int nchunk;           /* frequency chunks per data frame (48) */
+  int nch_per_chunk;    /* channels per chunk (7) */
+  int nsamp_df;         /* time samples per data frame (128) */
+  int big_endian;       /* 1: BMF wire order (hdr.c:15 byte-swaps; cudautil.cuh:118) */
+  float scale;          /* output = (float)sum * scale; 1 = integral (README.md:2),
+                           2^-20 = time average (paf_baseband2power.cu:20) */
+  int mode;             /* B2P_MODE_* */
+  int nbeam;            /* independent beam streams batched in this context (>=1) */
+  int kernel;           /* B2P_KERNEL_* */
+  int nsplit;           /* time splits per chunk (0 = auto from SM count) */
+  uint64_t stage_ndf;   /* data frames per H2D staging piece (0 = default 256) */
+  int nstage_bufs;      /* device staging buffers for the host path (0 = default 3) */
+} b2p_params;
+
+/* Fill *p with the reference pipeline's defaults (one beam, exact mode, scale 1). */
+void b2p_default_params(b2p_params *p);
+
+/*
+ * Create / destroy a context: selects the device, allocates the per-beam
+ * uint64 accumulators, the partial-sum scratch, streams, events and (lazily)
+ * the staging buffers.  Replaces the never-written init_baseband2power /
+ * destroy_baseband2power (siblings: diskdb.cuh:32-33).
+ */
+int  b2p_create(b2p_ctx **out, const b2p_params *p);
+void b2p_destroy(b2p_ctx *ctx);
+
+/* Message of the last failure on ctx (ctx == NULL: last b2p_create failure). */
+const char *b2p_last_error(const b2p_ctx *ctx);
+
+/*
+ * Unpack + detect + integrate `ndf` data frames per beam that already sit in
+ * device memory: dptrs[b] points at beam b's frames in ring-block layout
+ * block[idf][chunk][t][ch][pol][re,im] (capture.c:540-542).  Adds into the
+ * context's accumulators; asynchronous on `stream`.  An integration is any
+ * sequence of accumulate calls closed by b2p_finish*.
+ */
+int b2p_accumulate_device(b2p_ctx *ctx, const void *const *dptrs, uint64_t ndf, void *stream);
+
+/*
+ * Same, from host memory (a ring-buffer block returned by
+ * ipcio_open_block_read): frames are cut into pieces of stage_ndf, copied
+ * H2D on a copy stream into rotating staging buffers and reduced on the
+ * compute stream, copy k+1 overlapping kernel k.  hptrs[b] should be pinned
+ * (b2p_host_alloc / b2p_host_register, the role dada_cuda_dbregister from
+ * dada_cuda.h — included at baseband2power.cuh:9 — was to play); pageable
+ * memory works but the copies serialise.  Returns once every piece has been
+ * consumed (the caller may then release the ring block).
+ */
+int b2p_accumulate_host(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf);
+
+/*
+ * Zero-copy variant: the fused kernel reads the pinned, device-mapped host
+ * block directly over PCIe (no staging, one launch).  hptrs[b] must be pinned
+ * with b2p_host_alloc/b2p_host_register.  Synchronous like b2p_accumulate_host.
+ */
+int b2p_accumulate_host_mapped(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf);
+
+/*
+ * Close the integration: out[b*nchan + k] = (float)sum[b][k] * scale for
+ * k = chunk*nch_per_chunk + ch ascending — the 1344-byte output ring block
+ * (NCHAN*NBYTE, paf-baseband2power.conf:24-25; NBIT 32 / NDIM 1 / NPOL 1,
+ * header_baseband2power.txt:39-41) — and reset the accumulators.
+ * b2p_finish copies to host memory and synchronises; b2p_finish_device writes
+ * device memory asynchronously on `stream`.
+ */
+int b2p_finish(b2p_ctx *ctx, float *out_host);
+int b2p_finish_device(b2p_ctx *ctx, float *out_dev, void *stream);
+
+/* Copy the exact uint64 sums [nbeam*nchan] to the host without resetting (exact mode). */
+int b2p_read_sums(b2p_ctx *ctx, uint64_t *sums_host);
+/* Zero the accumulators without producing output. */
+int b2p_reset(b2p_ctx *ctx);
+
+/* introspection */
+int      b2p_nchan(const b2p_ctx *ctx);            /* nchunk*nch_per_chunk */
+uint64_t b2p_frame_bytes(const b2p_ctx *ctx);      /* bytes of one data frame, all chunks */
+int      b2p_kernel_in_use(const b2p_ctx *ctx);    /* B2P_KERNEL_LDG / _TMA after AUTO */
+int      b2p_nsplit_in_use(const b2p_ctx *ctx);
+uint64_t b2p_launch_count(const b2p_ctx *ctx);     /* kernels launched by this context */
+void    *b2p_stream(const b2p_ctx *ctx);           /* the context's compute stream */
+const char *b2p_version(void);
+int      b2p_device_count(void);                   /* cudaGetDeviceCount, paf_baseband2power.cu:88 */
+int      b2p_device_info(int device, char *name, size_t name_len, int *sm_count,
+                         int *cc_major, int *cc_minor, uint64_t *mem_bytes);
+
+/*
+ * Per-launch timing of the fused kernel with CUDA events on the launching
+ * stream.  When enabled every fused launch is bracketed by an event pair;
+ * b2p_fused_time_ms synchronises, returns the summed duration and the number
+ * of launches since the last call, and clears the record.
+ */
+int b2p_set_timing(b2p_ctx *ctx, int enabled);
+int b2p_fused_time_ms(b2p_ctx *ctx, double *sum_ms, uint64_t *launches);
+
+/* host / device memory helpers (for ring registration, tests and the bench) */
+int b2p_host_alloc(void **p, size_t bytes);        /* pinned + mapped */
+int b2p_host_free(void *p);
+int b2p_host_register(void *p, size_t bytes);      /* dada_cuda_dbregister's role */
+int b2p_host_unregister(void *p);
+int b2p_device_alloc(int device, void **p, size_t bytes);
+int b2p_device_free(int device, void *p);
+int b2p_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+int b2p_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+int b2p_device_sync(int device);
+
+/*
+ * Fill device memory with the counter-based synthetic BMF stream of
+ * b2p_synth.h (byte-identical to the host generator).  Test/bench data only.
+ */
+int b2p_synth_fill_device(int device, void *dptr, uint64_t ndf, int nchunk, int nch_per_chunk,
+                          int nsamp_df, int big_endian, uint64_t seed, uint64_t first_word,
+                          int mode, void *stream);
+
+/* Unit-test hook: unpack all 65536 16-bit patterns with the kernel's PRMT path.
+   out_host[v] = sign-extended value decoded from pattern v (both lanes checked). */
+int b2p_selftest_unpack(int device, int big_endian, int32_t *out_host /* [65536] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2P_H */

@@ -1,0 +1,172 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — bit-exact.
+
+Integer sums are compared as uint64, the float32 output as raw bit patterns.
+Float mode: <= 1e-6 relative to the exact value (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from tests import kat
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["ldg", "tma"]
+
+
+def _run_device(b2p, block, ndf, kernel="ldg", nbeam=1, **kw):
+    st = b2p.Baseband2Power(kernel=kernel, nbeam=nbeam, **kw)
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    per = block.nbytes // nbeam
+    st.accumulate_device([dev.ptr + b * per for b in range(nbeam)], ndf)
+    sums = st.read_sums() if kw.get("mode", "exact") == "exact" else None
+    out = st.finish()
+    dev.free()
+    st.close()
+    return sums, out
+
+
+def test_unpack_all_65536_patterns(b2p):
+    v = np.arange(65536, dtype=np.uint32)
+    be = ((v & 0xFF) << 8 | (v >> 8)).astype(np.uint16).view(np.int16).astype(np.int32)
+    le = v.astype(np.uint16).view(np.int16).astype(np.int32)
+    assert np.array_equal(b2p.selftest_unpack(0, True), be)
+    assert np.array_equal(b2p.selftest_unpack(0, False), le)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("big_endian", [True, False])
+def test_kats(b2p, oracle_mod, kernel, big_endian):
+    for name, (block, want) in kat.all_kats(ndf=5, big_endian=big_endian).items():
+        sums, out = _run_device(b2p, block, 5, kernel, big_endian=big_endian)
+        assert np.array_equal(sums[0], want), (kernel, name)
+        assert np.array_equal(out[0].view(np.uint32), oracle_mod.finish(want).view(np.uint32)), name
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("ndf", [1, 2, 7, 8, 9, 37, 64, 300, 1000])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_synth_blocks_bit_exact(b2p, oracle_mod, kernel, ndf, mode):
+    block = oracle_mod.synth_fill(ndf, seed=20240517 + ndf, mode=mode)
+    want = oracle_mod.accumulate_omp(block)
+    sums, out = _run_device(b2p, block, ndf, kernel)
+    assert np.array_equal(sums[0], want)
+    assert np.array_equal(out[0].view(np.uint32), oracle_mod.finish(want).view(np.uint32))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("nsplit", [1, 3, 37, 200])
+def test_nsplit_does_not_change_the_answer(b2p, oracle_mod, kernel, nsplit):
+    block = oracle_mod.synth_fill(50, seed=3, mode=0)
+    want = oracle_mod.accumulate_omp(block)
+    sums, _ = _run_device(b2p, block, 50, kernel, nsplit=nsplit)
+    assert np.array_equal(sums[0], want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_scale_mean(b2p, oracle_mod, kernel):
+    block = oracle_mod.synth_fill(16, seed=8, mode=1)
+    want = oracle_mod.finish(oracle_mod.accumulate(block), 2.0 ** -20)
+    _, out = _run_device(b2p, block, 16, kernel, scale=2.0 ** -20)
+    assert np.array_equal(out[0].view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_multibeam_batched(b2p, oracle_mod, kernel):
+    nbeam, ndf = 5, 24
+    g = oracle_mod.Geometry()
+    blocks = [oracle_mod.synth_fill(ndf, seed=100 + b, mode=b % 2) for b in range(nbeam)]
+    sums, out = _run_device(b2p, np.concatenate(blocks), ndf, kernel, nbeam=nbeam)
+    for b in range(nbeam):
+        want = oracle_mod.accumulate_omp(blocks[b], g=g)
+        assert np.array_equal(sums[b], want), b
+        assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(want).view(np.uint32))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_integration_spans_calls_and_resets(b2p, oracle_mod, kernel):
+    g = oracle_mod.Geometry()
+    block = oracle_mod.synth_fill(40, seed=77, mode=1)
+    want = oracle_mod.accumulate_omp(block)
+    st = b2p.Baseband2Power(kernel=kernel)
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    for f0, n in [(0, 13), (13, 1), (14, 26)]:
+        st.accumulate_device([dev.ptr + f0 * g.frame_bytes], n)
+    assert np.array_equal(st.read_sums()[0], want)
+    out = st.finish()[0]
+    assert np.array_equal(out.view(np.uint32), oracle_mod.finish(want).view(np.uint32))
+    assert not st.read_sums().any()  # finish resets the integration
+    st.accumulate_device([dev], 40)
+    assert np.array_equal(st.finish()[0].view(np.uint32), out.view(np.uint32))  # idempotent
+    assert st.launch_count > 0
+    dev.free()
+    st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_path_staged(b2p, oracle_mod, kernel, pinned):
+    ndf = 70
+    block = oracle_mod.synth_fill(ndf, seed=31, mode=1)
+    want = oracle_mod.accumulate_omp(block)
+    st = b2p.Baseband2Power(kernel=kernel, stage_ndf=16, nstage_bufs=2)
+    if pinned:
+        pb = b2p.PinnedBuffer(block.nbytes)
+        pb.array[:] = block
+        src = pb
+    else:
+        src = block
+    st.accumulate_host([src], ndf)
+    assert np.array_equal(st.read_sums()[0], want)
+    st.accumulate_host([src], ndf)   # second block of the same integration
+    out = st.finish()[0]
+    assert np.array_equal(out.view(np.uint32), oracle_mod.finish(want * np.uint64(2)).view(np.uint32))
+    if pinned:
+        st.accumulate_host_mapped([src], ndf)
+        assert np.array_equal(st.read_sums()[0], want)
+        pb.free()
+    st.close()
+
+
+@pytest.mark.parametrize("geom", [(2, 3, 4), (5, 7, 16), (3, 1, 2), (4, 32, 6), (6, 8, 128), (48, 7, 64)])
+def test_other_geometries(b2p, oracle_mod, geom):
+    nchunk, nch, nsamp = geom
+    g = oracle_mod.Geometry(nchunk=nchunk, nch_per_chunk=nch, nsamp_df=nsamp)
+    ndf = 11
+    block = oracle_mod.synth_fill(ndf, seed=5, mode=0, g=g)
+    want = oracle_mod.accumulate(block, g=g)
+    sums, _ = _run_device(b2p, block, ndf, "ldg", nchunk=nchunk, nch_per_chunk=nch, nsamp_df=nsamp)
+    assert np.array_equal(sums[0], want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_float_mode_within_1e6(b2p, oracle_mod, kernel):
+    block = oracle_mod.synth_fill(256, seed=9, mode=1)
+    exact = oracle_mod.accumulate_omp(block).astype(np.float64)
+    _, out = _run_device(b2p, block, 256, kernel, mode="float")
+    rel = np.abs(out[0].astype(np.float64) - exact) / exact
+    assert rel.max() <= 1e-6, rel.max()   # tolerance stated by BASELINE.json north_star
+
+
+def test_device_synth_matches_host_generator(b2p, oracle_mod):
+    g = oracle_mod.Geometry()
+    for mode in (0, 1):
+        host = oracle_mod.synth_fill(3, seed=42, first_word=987654321, mode=mode)
+        dev = b2p.DeviceBuffer(host.nbytes)
+        dev.synth_fill(3, seed=42, first_word=987654321, mode=mode)
+        assert np.array_equal(dev.download(), host)
+        dev.free()
+
+
+def test_bad_arguments_fail_loudly(b2p):
+    with pytest.raises(b2p.B2pError):
+        b2p.Baseband2Power(nbeam=0)
+    with pytest.raises(b2p.B2pError):
+        b2p.Baseband2Power(nch_per_chunk=3, nsamp_df=1)  # packet not a multiple of 16 B
+    st = b2p.Baseband2Power()
+    with pytest.raises(b2p.B2pError):
+        st.accumulate_device([0], 4)       # NULL pointer
+    with pytest.raises(b2p.B2pError):
+        st.accumulate_device([8], 4)       # misaligned
+    st.close()
