@@ -15,7 +15,7 @@ def __getattr__(name):
     # the ABI binding is imported lazily so that `import paf_baseband2power_b200`
     # works for host-only helpers; using the stage without libb2p.so raises.
     if name in ("Baseband2Power", "PinnedBuffer", "DeviceBuffer", "B2pError", "device_count",
-                "device_info", "selftest_unpack"):
+                "device_info", "device_sync", "selftest_unpack"):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

@@ -49,6 +49,11 @@ def device_info(device: int = 0) -> dict:
             "mem_bytes": mem.value}
 
 
+def device_sync(device: int = 0):
+    """cudaDeviceSynchronize on `device` (the context streams are non-blocking streams)."""
+    _check(_lib.load().b2p_device_sync(device))
+
+
 class PinnedBuffer:
     """Pinned, device-mapped host memory (the ring block a reader would borrow)."""
 

@@ -28,6 +28,8 @@ struct b2p_ctx {
   int sm_count;
   int kernel; /* resolved */
   int nsplit; /* resolved */
+  int variant; /* tuning variant, B2P_VARIANT env (experiments) */
+  int no_early; /* B2P_NO_EARLY=1: never start a fused kernel before its predecessor ends */
   size_t acc_elem;
   cudaStream_t compute, copy;
   void *acc;
@@ -44,6 +46,11 @@ struct b2p_ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used;
   uint64_t launches;
+  /* partial sums of the last fused launch not yet folded into acc */
+  int pending;
+  B2pSlots pend_slots;
+  int pend_nsplit;
+  cudaStream_t pend_stream;
   char err[512];
 };
 
@@ -141,16 +148,23 @@ static int resolve_kernel(const b2p_params *p)
 static int resolve_nsplit(const b2p_params *p, int kernel, int sm_count)
 {
   if (p->nsplit > 0) return p->nsplit > 1024 ? 1024 : p->nsplit;
-  unsigned slots, units;
+  /* base = smallest split count that makes the grid a whole number of waves;
+     LDG: 4 CTAs/SM and ~37 frames per CTA measured best (18 waves for one beam). */
+  unsigned slots, units, target;
   if (kernel == B2P_KERNEL_TMA) {
     slots = (unsigned)sm_count;
     units = (unsigned)(p->nchunk / b2p_tma_group(p->nchunk)) * (unsigned)p->nbeam;
+    target = 37;
   } else {
-    slots = 2u * (unsigned)sm_count;
+    slots = 4u * (unsigned)sm_count;
     units = (unsigned)p->nchunk * (unsigned)p->nbeam;
+    target = 222; /* 8192 frames / 222 = 37 frames per CTA */
   }
-  unsigned n = slots / gcd_u(slots, units); /* smallest n with n*units % slots == 0 */
-  if (n > 256) n = 256;
+  const unsigned base = slots / gcd_u(slots, units); /* smallest n with n*units % slots == 0 */
+  unsigned k = (target + base / 2) / base;
+  if (k < 1) k = 1;
+  unsigned n = base * k;
+  if (n > 1024) n = 1024;
   if (n < 1) n = 1;
   return (int)n;
 }
@@ -192,6 +206,9 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   c->timing = 0;
   c->ev_used = 0;
   c->launches = 0;
+  c->pending = 0;
+  c->pend_nsplit = 0;
+  c->pend_stream = NULL;
   c->nbufs = 0;
   c->acc = c->partials = NULL;
   c->out_dev = c->out_pinned = NULL;
@@ -216,6 +233,8 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(b2p_kernels_configure());
   c->kernel = resolve_kernel(p);
   c->nsplit = resolve_nsplit(p, c->kernel, c->sm_count);
+  c->variant = getenv("B2P_VARIANT") ? atoi(getenv("B2P_VARIANT")) : 0;
+  c->no_early = getenv("B2P_NO_EARLY") ? atoi(getenv("B2P_NO_EARLY")) : 0;
   CKC(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
   const size_t nacc = (size_t)p->nbeam * c->nchan;
@@ -258,18 +277,56 @@ int b2p_nsplit_in_use(const b2p_ctx *c) { return c ? c->nsplit : 0; }
 uint64_t b2p_launch_count(const b2p_ctx *c) { return c ? c->launches : 0; }
 void *b2p_stream(const b2p_ctx *c) { return c ? (void *)c->compute : NULL; }
 
-/* fused + finalize for `n` beams on `st`; ptrs/slots describe the launch's beams */
-static int launch_pair(b2p_ctx *c, const void *const *ptrs, const int *slots, int n, uint64_t ndf,
-                       int kernel, cudaStream_t st)
+/* Fold the pending partial sums into the accumulators (finish=0) or emit the
+   spectrum and clear (finish=1).  One kernel either way. */
+static int launch_reduce(b2p_ctx *c, int finish, float *out, cudaStream_t st)
+{
+  B2pReduce R;
+  memset(&R, 0, sizeof(R));
+  if (c->pending)
+    R.slots = c->pend_slots;
+  else
+    for (int i = 0; i < B2P_MAX_BEAMS; ++i) R.slots.lb[i] = -1;
+  R.nrows = c->p.nbeam;
+  R.nsplit = c->pending ? c->pend_nsplit : 0;
+  R.nchan = c->nchan;
+  R.mode = c->p.mode;
+  R.finish = finish;
+  R.pdl = 1;
+  R.partials = c->partials;
+  R.acc = c->acc;
+  R.out = out;
+  R.scale = c->p.scale;
+  CK(c, b2p_launch_reduce(R, st));
+  c->pending = 0;
+  c->launches += 1;
+  return B2P_OK;
+}
+
+static int flush_pending(b2p_ctx *c, cudaStream_t st)
+{
+  if (!c->pending) return B2P_OK;
+  if (c->pend_stream != st) CK(c, cudaStreamSynchronize(c->pend_stream));
+  return launch_reduce(c, 0, NULL, st);
+}
+
+/* One fused launch for `n` beams on `st`; its partial sums stay pending until the
+   next accumulate (folded into acc first) or finish (folded and converted at once). */
+static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, int n, uint64_t ndf,
+                        int kernel, cudaStream_t st)
 {
   B2pLaunch L;
   memset(&L, 0, sizeof(L));
+  const uintptr_t align_mask = b2p_is_bmf_geometry(c->p.nch_per_chunk, c->p.nsamp_df) ? 31u : 15u;
   for (int b = 0; b < n; ++b) {
     if (!ptrs[b]) FAIL(c, B2P_EINVAL, "accumulate: NULL beam pointer");
-    if (((uintptr_t)ptrs[b]) & 15u) FAIL(c, B2P_EINVAL, "accumulate: beam pointer not 16-byte aligned");
+    if (((uintptr_t)ptrs[b]) & align_mask)
+      FAIL(c, B2P_EINVAL, "accumulate: beam pointer misaligned (32 bytes for the BMF geometry, else 16)");
     L.beams.ptr[b] = ptrs[b];
     L.beams.slot[b] = slots ? slots[b] : b;
   }
+  int rc = flush_pending(c, st);
+  if (rc) return rc;
   L.nbeam = n;
   L.nchunk = c->p.nchunk;
   L.nch = c->p.nch_per_chunk;
@@ -278,11 +335,17 @@ static int launch_pair(b2p_ctx *c, const void *const *ptrs, const int *slots, in
   L.mode = c->p.mode;
   L.kernel = kernel;
   L.sm_count = c->sm_count;
+  L.variant = c->variant;
+  L.calib = getenv("B2P_CALIB") ? atoi(getenv("B2P_CALIB")) : 0;
+  L.pdl = 1;
+  /* Only on the context's own stream is it known that the input was complete before
+     the call: there the kernel may start while its predecessor is still running. */
+  L.early = (st == c->compute && !c->no_early) ? 1 : 0;
   L.ndf = ndf;
   L.partials = c->partials;
   L.acc = c->acc;
-  /* short launches: never give a CTA fewer than 8 frames if it can be helped */
-  uint64_t ns = ndf / 8;
+  /* short launches: never give a CTA fewer than 16 frames if it can be helped */
+  uint64_t ns = ndf / 16;
   if (ns < 1) ns = 1;
   if (ns > (uint64_t)c->nsplit) ns = (uint64_t)c->nsplit;
   L.nsplit = (int)ns;
@@ -301,8 +364,12 @@ static int launch_pair(b2p_ctx *c, const void *const *ptrs, const int *slots, in
   }
   CK(c, b2p_launch_fused(L, st));
   if (c->timing) CK(c, cudaEventRecord(e1, st));
-  CK(c, b2p_launch_finalize(L, st));
-  c->launches += 2;
+  c->launches += 1;
+  c->pending = 1;
+  c->pend_nsplit = L.nsplit;
+  c->pend_stream = st;
+  for (int i = 0; i < B2P_MAX_BEAMS; ++i) c->pend_slots.lb[i] = -1;
+  for (int b = 0; b < n; ++b) c->pend_slots.lb[L.beams.slot[b]] = b;
   return B2P_OK;
 }
 
@@ -313,7 +380,7 @@ int b2p_accumulate_device(b2p_ctx *c, const void *const *dptrs, uint64_t ndf, vo
   if (ndf == 0) return B2P_OK;
   CK(c, cudaSetDevice(c->p.device_id));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->compute;
-  return launch_pair(c, dptrs, NULL, c->p.nbeam, ndf, c->kernel, st);
+  return launch_fused(c, dptrs, NULL, c->p.nbeam, ndf, c->kernel, st);
 }
 
 static int ensure_staging(b2p_ctx *c)
@@ -355,7 +422,7 @@ int b2p_accumulate_host(b2p_ctx *c, const void *const *hptrs, uint64_t ndf)
       CK(c, cudaEventRecord(c->copied[buf], c->copy));
       CK(c, cudaStreamWaitEvent(c->compute, c->copied[buf], 0));
       const void *ptr = c->stage[buf];
-      rc = launch_pair(c, &ptr, &b, 1, n, c->kernel, c->compute);
+      rc = launch_fused(c, &ptr, &b, 1, n, c->kernel, c->compute);
       if (rc) return rc;
       CK(c, cudaEventRecord(c->consumed[buf], c->compute));
       c->pieces++;
@@ -379,7 +446,7 @@ int b2p_accumulate_host_mapped(b2p_ctx *c, const void *const *hptrs, uint64_t nd
     CK(c, cudaHostGetDevicePointer(&d, (void *)hptrs[b], 0));
     dptrs[b] = d;
   }
-  int rc = launch_pair(c, dptrs, NULL, c->p.nbeam, ndf, B2P_KERNEL_LDG, c->compute);
+  int rc = launch_fused(c, dptrs, NULL, c->p.nbeam, ndf, B2P_KERNEL_LDG, c->compute);
   if (rc) return rc;
   CK(c, cudaStreamSynchronize(c->compute)); /* the kernel reads the host block itself */
   return B2P_OK;
@@ -391,9 +458,8 @@ int b2p_finish_device(b2p_ctx *c, float *out_dev, void *stream)
   if (!out_dev) FAIL(c, B2P_EINVAL, "b2p_finish_device: NULL output");
   CK(c, cudaSetDevice(c->p.device_id));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->compute;
-  CK(c, b2p_launch_finish(c->acc, out_dev, c->p.nbeam * c->nchan, c->p.scale, c->p.mode, st));
-  c->launches += 1;
-  return B2P_OK;
+  if (c->pending && c->pend_stream != st) CK(c, cudaStreamSynchronize(c->pend_stream));
+  return launch_reduce(c, 1, out_dev, st);
 }
 
 int b2p_finish(b2p_ctx *c, float *out_host)
@@ -415,6 +481,12 @@ int b2p_read_sums(b2p_ctx *c, uint64_t *sums_host)
   if (!sums_host) FAIL(c, B2P_EINVAL, "b2p_read_sums: NULL output");
   if (c->p.mode != B2P_MODE_EXACT) FAIL(c, B2P_ESTATE, "b2p_read_sums: exact mode only");
   CK(c, cudaSetDevice(c->p.device_id));
+  if (c->pending) {
+    cudaStream_t ps = c->pend_stream;
+    int rc = flush_pending(c, ps);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(ps));
+  }
   CK(c, cudaStreamSynchronize(c->compute));
   CK(c, cudaMemcpy(sums_host, c->acc, (size_t)c->p.nbeam * c->nchan * 8, cudaMemcpyDeviceToHost));
   return B2P_OK;
@@ -424,6 +496,10 @@ int b2p_reset(b2p_ctx *c)
 {
   if (!c) return B2P_EINVAL;
   CK(c, cudaSetDevice(c->p.device_id));
+  if (c->pending) {
+    CK(c, cudaStreamSynchronize(c->pend_stream));
+    c->pending = 0;
+  }
   CK(c, cudaMemsetAsync(c->acc, 0, (size_t)c->p.nbeam * c->nchan * c->acc_elem, c->compute));
   CK(c, cudaStreamSynchronize(c->compute));
   return B2P_OK;

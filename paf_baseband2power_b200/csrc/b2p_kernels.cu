@@ -13,11 +13,13 @@
  * The op is a streaming reduction, ~1 integer op per input byte, no reuse:
  * HBM-bound, tensor cores irrelevant.  Two fused variants:
  *
- *   LDG  one CTA = (time split, chunk, beam), 448 threads; thread j owns the
- *        j-th 16-byte unit of every packet of its chunk, i.e. payload words 2j
- *        and 2j+1, whose channels (2j)%7 and (2j+1)%7 never change -> two
- *        register accumulators, fully coalesced 7168-B rows, UNROLL independent
- *        128-bit streaming loads in flight per thread.
+ *   LDG  one CTA = (chunk, time split, beam), 224 threads; thread j owns the
+ *        j-th 32-byte unit of every packet of its chunk, i.e. payload words
+ *        4j..4j+3, whose channels (4j+k)%7 never change -> four register
+ *        accumulators, fully coalesced 7168-B rows, 4 independent 256-bit
+ *        streaming loads (LDG.E.256, L2 evict-first) in flight per thread, 4
+ *        CTAs per SM.  A 128-bit form of the same scheme serves other
+ *        geometries and is kept as a tuning point (B2P_VARIANT=1).
  *   TMA  persistent CTAs (one per SM): a producer lane streams G consecutive
  *        packets (G*7168 contiguous bytes, one cp.async.bulk) per stage into an
  *        NSTAGE-deep shared-memory ring guarded by full/empty mbarriers; 448
@@ -28,10 +30,18 @@
  * Detect/integrate (exact mode): IMAD squares, a pair of squares fits uint32
  * (<= 2^31), words are accumulated in uint64 — a channel total is <= 2^52, so
  * the sum is exact and independent of order; CTA partials go to global memory
- * and a second tiny kernel adds them in index order (no atomics anywhere).
+ * and a second tiny kernel (one warp per channel) adds them and either updates
+ * the running accumulator or emits the float32 spectrum.  No atomics anywhere.
+ *
+ * Launch chaining: every kernel is launched with programmatic stream
+ * serialization (PDL).  A fused kernel releases its dependents at once and only
+ * waits for its predecessor (griddepcontrol.wait) right before it writes its
+ * partial sums, so on the context's own stream the head of integration N+1
+ * overlaps the tail of integration N and the launch gaps disappear.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/b2p_synth.h"
 #include "b2p_kernels.cuh"
@@ -41,10 +51,20 @@ namespace {
 constexpr int kUnitsBmf = 448;        /* 16-byte units per 7168-byte packet */
 constexpr int kPktBytes = 7168;
 constexpr int kNchBmf = 7;
-constexpr int kLdgUnroll = 8;
 constexpr int kTmaConsumers = kUnitsBmf;           /* 14 warps */
 constexpr int kTmaThreads = kTmaConsumers + 32;    /* + 1 producer warp */
 constexpr int kTmaConsumerWarps = kTmaConsumers / 32;
+
+/* ------------------------------------------------- programmatic launch (PDL) */
+
+__device__ __forceinline__ void pdl_release_dependents()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_predecessor()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 /* ------------------------------------------------------------------ unpack */
 
@@ -112,6 +132,22 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
   return r;
 }
 
+/* Blackwell's 256-bit global load carries an L2 eviction priority: the block is
+   read exactly once, so its lines are marked evict-first (SASS LDG.E.NA.EFL2.256). */
+struct u32x8 {
+  uint32_t r[8];
+};
+__device__ __forceinline__ u32x8 ldg256_stream(const void *p)
+{
+  u32x8 v;
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]),
+        "=r"(v.r[6]), "=r"(v.r[7])
+      : "l"(p));
+  return v;
+}
+
 /* frames [f0,f1) of time split `s` out of `n` */
 __device__ __forceinline__ void split_range(uint64_t ndf, uint32_t s, uint32_t n, uint64_t &f0,
                                             uint64_t &f1)
@@ -121,18 +157,20 @@ __device__ __forceinline__ void split_range(uint64_t ndf, uint32_t s, uint32_t n
 }
 
 /*
- * CTA reduction of per-thread accumulators a0 (channel c0) and a1 (channel c1)
- * into nch channel totals, written to dst[0..nch).  `red` is [nwarps][nch].
- * Every add is integer (exact mode) so the order is immaterial; in float mode
- * the order is fixed by construction (xor tree, then warps ascending).
+ * CTA reduction of NA per-thread accumulators a[i] (channel c[i]) into nch
+ * channel totals, written to dst[0..nch).  `red` is [nwarps][nch].  Every add
+ * is integer (exact mode) so the order is immaterial; in float mode the order is
+ * fixed by construction (xor tree, then warps ascending).
  */
-template <typename T>
-__device__ __forceinline__ void cta_reduce_channels(T a0, T a1, int c0, int c1, int nch, T *red,
-                                                    T *dst, int tid, int nthreads)
+template <typename T, int NA>
+__device__ __forceinline__ void cta_reduce_n(const T (&a)[NA], const int (&c)[NA], int nch, T *red,
+                                             T *dst, int tid, int nthreads)
 {
   const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
   for (int ch = 0; ch < nch; ++ch) {
-    T v = (c0 == ch ? a0 : (T)0) + (c1 == ch ? a1 : (T)0);
+    T v = 0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) v += (c[i] == ch ? a[i] : (T)0);
     v = warp_sum(v);
     if (lane == 0) red[warp * nch + ch] = v;
   }
@@ -144,76 +182,138 @@ __device__ __forceinline__ void cta_reduce_channels(T a0, T a1, int c0, int c1, 
   }
 }
 
-/* ------------------------------------------------ LDG kernel, BMF geometry */
-
-template <typename Acc, bool BE, int UNROLL>
-__global__ void __launch_bounds__(kUnitsBmf, 2)
-b2p_fused_ldg_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t ndf,
-                  typename Acc::type *__restrict__ partials)
+/* ------------------------------------- LDG.256 kernel, BMF geometry (default) */
+/*
+ * 224 threads cover a 7168-byte packet with 32 bytes each = payload words
+ * 4j..4j+3, channels (4j+k)%7: four register accumulators per thread.  UF frames
+ * are unrolled, so UF independent 256-bit loads are in flight per thread.  The
+ * chunk index is blockIdx.x, so CTAs that run together read adjacent packets of
+ * the same frames.  `early`: the input does not depend on the preceding kernel of
+ * the stream, so only the partial-sum store has to wait for it.
+ */
+template <typename Acc, bool BE, int UF, int MINB>
+__global__ void __launch_bounds__(224, MINB)
+b2p_fused_ldg256_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t ndf,
+                     const int early, typename Acc::type *__restrict__ partials)
 {
   typedef typename Acc::type T;
-  __shared__ T red[(kUnitsBmf / 32) * kNchBmf];
+  constexpr int THREADS = 224;
+  __shared__ T red[(THREADS / 32) * kNchBmf];
+  pdl_release_dependents();
+  if (!early) pdl_wait_predecessor();
   const int j = threadIdx.x;
-  const uint32_t split = blockIdx.x, nsplit = gridDim.x, chunk = blockIdx.y, beam = blockIdx.z;
+  const uint32_t chunk = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y, beam = blockIdx.z;
   uint64_t f0, f1;
   split_range(ndf, split, nsplit, f0, f1);
-
-  const size_t fstride = (size_t)nchunk * kUnitsBmf; /* uint4 units per data frame */
-  const uint4 *p = (const uint4 *)beams.ptr[beam] + (f0 * nchunk + chunk) * kUnitsBmf + j;
-  T a0 = 0, a1 = 0;
+  const size_t fstride = (size_t)nchunk * kPktBytes; /* bytes per data frame */
+  const unsigned char *p =
+      (const unsigned char *)beams.ptr[beam] + (f0 * nchunk + chunk) * kPktBytes + j * 32;
+  T a[4] = {0, 0, 0, 0};
   uint64_t f = f0;
-  for (; f + UNROLL <= f1; f += UNROLL) {
-    uint4 v[UNROLL];
+  for (; f + UF <= f1; f += UF) {
+    u32x8 v[UF];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(p + u * fstride);
-    p += UNROLL * fstride;
+    for (int u = 0; u < UF; ++u) v[u] = ldg256_stream(p + u * fstride);
+    p += UF * fstride;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      Acc::template add<BE>(a0, v[u].x, v[u].y);
-      Acc::template add<BE>(a1, v[u].z, v[u].w);
-    }
+    for (int u = 0; u < UF; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Acc::template add<BE>(a[k], v[u].r[2 * k], v[u].r[2 * k + 1]);
   }
   for (; f < f1; ++f) {
-    uint4 v = ldg_stream(p);
+    u32x8 v = ldg256_stream(p);
     p += fstride;
-    Acc::template add<BE>(a0, v.x, v.y);
-    Acc::template add<BE>(a1, v.z, v.w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Acc::template add<BE>(a[k], v.r[2 * k], v.r[2 * k + 1]);
   }
   const size_t nchan = (size_t)nchunk * kNchBmf;
   T *dst = partials + ((size_t)beam * nsplit + split) * nchan + (size_t)chunk * kNchBmf;
-  cta_reduce_channels<T>(a0, a1, (2 * j) % kNchBmf, (2 * j + 1) % kNchBmf, kNchBmf, red, dst, j,
-                         kUnitsBmf);
+  const int c[4] = {(4 * j) % kNchBmf, (4 * j + 1) % kNchBmf, (4 * j + 2) % kNchBmf,
+                    (4 * j + 3) % kNchBmf};
+  if (early) pdl_wait_predecessor(); /* the previous reduce kernel has consumed `partials` */
+  cta_reduce_n<T, 4>(a, c, kNchBmf, red, dst, j, THREADS);
 }
 
-/* ------------------------------------------------ LDG kernel, any geometry */
-/* blockDim.x = 32*nch so that 2*blockDim.x is a multiple of nch: the channels of
-   a thread's two words are fixed although it walks several units per packet. */
-template <typename Acc, bool BE>
-__global__ void b2p_fused_ldg_any(const B2pBeams beams, const uint32_t nchunk, const uint32_t nch,
-                                  const uint32_t units_per_pkt, const uint64_t ndf,
-                                  typename Acc::type *__restrict__ partials)
+/* ------------------------------------------------ LDG.128 kernel, any geometry */
+/*
+ * blockDim.x is a multiple of nch (32*nch, or 448 for the BMF packet), so
+ * 2*blockDim.x is too: the channels of a thread's two words are fixed although it
+ * may walk several 16-byte units per packet.  UF frames unrolled.  CALIB replaces
+ * unpack/detect by an XOR (bandwidth calibration only, B2P_CALIB=1).
+ */
+template <typename Acc, bool BE, int UF, bool CALIB>
+__global__ void b2p_fused_ldg128(const B2pBeams beams, const uint32_t nchunk, const uint32_t nch,
+                                 const uint32_t units_per_pkt, const uint64_t ndf, const int early,
+                                 typename Acc::type *__restrict__ partials)
 {
   typedef typename Acc::type T;
   extern __shared__ __align__(16) unsigned char smem_any[];
   T *red = (T *)smem_any;
+  pdl_release_dependents();
+  if (!early) pdl_wait_predecessor();
   const int j = threadIdx.x, nt = blockDim.x;
-  const uint32_t split = blockIdx.x, nsplit = gridDim.x, chunk = blockIdx.y, beam = blockIdx.z;
+  const uint32_t chunk = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y, beam = blockIdx.z;
   uint64_t f0, f1;
   split_range(ndf, split, nsplit, f0, f1);
-  const uint4 *base = (const uint4 *)beams.ptr[beam];
+  const size_t fstride = (size_t)nchunk * units_per_pkt;
+  const uint4 *base = (const uint4 *)beams.ptr[beam] + (f0 * nchunk + chunk) * units_per_pkt;
   T a0 = 0, a1 = 0;
-  for (uint64_t f = f0; f < f1; ++f) {
-    const uint4 *pkt = base + (f * nchunk + chunk) * units_per_pkt;
-#pragma unroll 4
-    for (uint32_t u = j; u < units_per_pkt; u += nt) {
-      uint4 v = ldg_stream(pkt + u);
+  for (uint32_t u = j; u < units_per_pkt; u += nt) {
+    const uint4 *p = base + u;
+    uint64_t f = f0;
+    for (; f + UF <= f1; f += UF) {
+      uint4 v[UF];
+#pragma unroll
+      for (int k = 0; k < UF; ++k) v[k] = ldg_stream(p + k * fstride);
+      p += UF * fstride;
+#pragma unroll
+      for (int k = 0; k < UF; ++k) {
+        if (CALIB) {
+          a0 += (T)(v[k].x ^ v[k].y);
+          a1 += (T)(v[k].z ^ v[k].w);
+        } else {
+          Acc::template add<BE>(a0, v[k].x, v[k].y);
+          Acc::template add<BE>(a1, v[k].z, v[k].w);
+        }
+      }
+    }
+    for (; f < f1; ++f) {
+      uint4 v = ldg_stream(p);
+      p += fstride;
       Acc::template add<BE>(a0, v.x, v.y);
       Acc::template add<BE>(a1, v.z, v.w);
     }
   }
   const size_t nchan = (size_t)nchunk * nch;
   T *dst = partials + ((size_t)beam * nsplit + split) * nchan + (size_t)chunk * nch;
-  cta_reduce_channels<T>(a0, a1, (2 * j) % nch, (2 * j + 1) % nch, nch, red, dst, j, nt);
+  const T a[2] = {a0, a1};
+  const int c[2] = {(int)((2 * j) % nch), (int)((2 * j + 1) % nch)};
+  if (early) pdl_wait_predecessor();
+  cta_reduce_n<T, 2>(a, c, (int)nch, red, dst, j, nt);
+}
+
+/* Bandwidth calibration only (B2P_CALIB=1): flat grid-stride read of the block,
+   no unpack/detect; tells how close the real kernels sit to a plain streaming read. */
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+b2p_calib_flat(const B2pBeams beams, const uint64_t nunits, T *__restrict__ partials)
+{
+  const uint4 *p = (const uint4 *)beams.ptr[blockIdx.y];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t x = 0;
+  for (; i + 7 * stride < nunits; i += 8 * stride) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = ldg_stream(p + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+  }
+  for (; i < nunits; i += stride) {
+    uint4 v = ldg_stream(p + i);
+    x ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (x == 0x12345678u) partials[0] = (T)x; /* keep the loads alive */
 }
 
 /* --------------------------------------------------- TMA / mbarrier helpers */
@@ -292,7 +392,7 @@ template <int G, int NSTAGE> struct TmaSmem {
 template <typename Acc, bool BE, int G, int NSTAGE>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t ndf,
-                  const uint32_t nsplit, const uint32_t nitems,
+                  const uint32_t nsplit, const uint32_t nitems, const int early,
                   typename Acc::type *__restrict__ partials)
 {
   typedef typename Acc::type T;
@@ -304,6 +404,7 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ngroups = nchunk / G;
+  pdl_release_dependents();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
@@ -311,6 +412,7 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
     }
     mbar_fence_init();
   }
+  if (!early) pdl_wait_predecessor();
   __syncthreads();
 
   if (warp == kTmaConsumerWarps) {
@@ -340,6 +442,7 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
   const int c0 = (2 * tid) % kNchBmf, c1 = (2 * tid + 1) % kNchBmf;
   const size_t nchan = (size_t)nchunk * kNchBmf;
   uint32_t it = 0;
+  bool waited = !early;
   for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
     const uint32_t group = item % ngroups, rest = item / ngroups;
     const uint32_t split = rest % nsplit, beam = rest / nsplit;
@@ -376,42 +479,58 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
       }
     consumer_bar();
     if (tid < G * kNchBmf) {
+      if (!waited) pdl_wait_predecessor();
       T sum = 0;
       for (int w = 0; w < kTmaConsumerWarps; ++w) sum += red[w * (G * kNchBmf) + tid];
       dst[tid] = sum;
     }
+    waited = true;
     consumer_bar(); /* red is reused by the next item */
   }
 }
 
-/* ----------------------------------------------------- finalize and finish */
+/* -------------------------------------------- cross-CTA reduce and finish */
 
-/* acc[slot[b]][k] += sum over splits (ascending) of partials[b][split][k] */
-template <typename T>
-__global__ void b2p_finalize(const B2pBeams beams, const uint32_t nsplit, const uint32_t nchan,
-                             const T *__restrict__ partials, T *__restrict__ acc)
-{
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, beam = blockIdx.y;
-  if (k >= nchan) return;
-  const T *p = partials + (size_t)beam * nsplit * nchan + k;
-  T s = 0;
-  for (uint32_t i = 0; i < nsplit; ++i) s += p[(size_t)i * nchan];
-  acc[(size_t)beams.slot[beam] * nchan + k] += s;
-}
-
-/* out = (float)sum * scale (one RN conversion, one fp32 multiply), then clear */
 __device__ __forceinline__ float to_f32_rn(unsigned long long v) { return __ull2float_rn(v); }
 __device__ __forceinline__ float to_f32_rn(double v) { return __double2float_rn(v); }
 
-template <typename T>
-__global__ void b2p_finish_k(T *__restrict__ acc, float *__restrict__ out, const int n,
-                             const float scale)
+/*
+ * One warp per (accumulator row, channel): lanes stride over the time splits of
+ * the row's pending partial sums (if any), a fixed xor tree joins them, lane 0
+ * adds the running accumulator.  FINISH: emit (float)total*scale (one RN
+ * conversion, one fp32 multiply) and clear the accumulator; otherwise store the
+ * total back.  Replaces any atomic cross-block reduction.
+ */
+template <typename T, bool FINISH>
+__global__ void __launch_bounds__(256)
+b2p_reduce_k(const B2pSlots slots, const uint32_t nrows, const uint32_t nsplit,
+             const uint32_t nchan, const T *__restrict__ partials, T *__restrict__ acc,
+             float *__restrict__ out, const float scale)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const T v = acc[i];
-  acc[i] = 0;
-  out[i] = __fmul_rn(to_f32_rn(v), scale);
+  pdl_release_dependents();
+  pdl_wait_predecessor();
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nrows * nchan) return;
+  const uint32_t row = w / nchan, k = w % nchan;
+  const int lb = slots.lb[row];
+  T s = 0;
+  if (lb >= 0) {
+    const T *p = partials + (size_t)lb * nsplit * nchan + k;
+    for (uint32_t i = lane; i < nsplit; i += 32) s += p[(size_t)i * nchan];
+    s = warp_sum(s);
+  } else if (!FINISH) {
+    return;
+  }
+  if (lane == 0) {
+    const size_t idx = (size_t)row * nchan + k;
+    const T total = acc[idx] + s;
+    if (FINISH) {
+      out[idx] = __fmul_rn(to_f32_rn(total), scale);
+      acc[idx] = 0;
+    } else {
+      acc[idx] = total;
+    }
+  }
 }
 
 /* ------------------------------------------------------- synthetic stream */
@@ -442,6 +561,25 @@ template <bool BE> __global__ void b2p_selftest_unpack_k(int32_t *out)
   out[v] = (lo == hi) ? lo : (int32_t)0x7FFFFFFF;
 }
 
+/* ------------------------------------------------------------ launch helper */
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     bool pdl, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 } /* namespace */
 
 /* ======================================================================== host */
@@ -464,16 +602,16 @@ cudaError_t launch_tma(const B2pLaunch &L, cudaStream_t st)
   const uint32_t nitems = (uint32_t)L.nbeam * L.nsplit * ngroups;
   uint32_t grid = (uint32_t)L.sm_count;
   if (grid > nitems) grid = nitems;
-  b2p_fused_tma_bmf<Acc, BE, G, NSTAGE><<<grid, kTmaThreads, S::kBytes, st>>>(
-      L.beams, (uint32_t)L.nchunk, L.ndf, (uint32_t)L.nsplit, nitems,
-      (typename Acc::type *)L.partials);
-  return cudaGetLastError();
+  return launch_k(b2p_fused_tma_bmf<Acc, BE, G, NSTAGE>, dim3(grid), dim3(kTmaThreads), S::kBytes,
+                  st, L.pdl != 0, L.beams, (uint32_t)L.nchunk, L.ndf, (uint32_t)L.nsplit, nitems,
+                  L.early, (typename Acc::type *)L.partials);
 }
 
 template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, cudaStream_t st)
 {
   typedef typename Acc::type T;
   const bool bmf = b2p_is_bmf_geometry(L.nch, L.nsamp);
+  const bool pdl = L.pdl != 0;
   if (L.kernel == B2P_KERNEL_TMA && bmf) {
     switch (b2p_tma_group(L.nchunk)) {
       case 4: return launch_tma<Acc, BE, 4, kTmaStagesG4>(L, st);
@@ -481,18 +619,33 @@ template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, 
       default: return launch_tma<Acc, BE, 1, kTmaStagesG1>(L, st);
     }
   }
-  dim3 grid((unsigned)L.nsplit, (unsigned)L.nchunk, (unsigned)L.nbeam);
+  const dim3 grid((unsigned)L.nchunk, (unsigned)L.nsplit, (unsigned)L.nbeam);
+  T *part = (T *)L.partials;
+  if (bmf && L.calib && L.variant == 9) /* calibration only: flat streaming read */
+    return launch_k(b2p_calib_flat<T>, dim3(4 * L.sm_count, L.nbeam), dim3(256), 0, st, false,
+                    L.beams, L.ndf * (uint64_t)L.nchunk * kUnitsBmf, part);
+  if (bmf && L.calib && L.variant == 7) /* calibration only: same pattern, loads + XOR */
+    return launch_k(b2p_fused_ldg128<Acc, BE, 8, true>, grid, dim3(448), 14 * 7 * sizeof(T), st,
+                    pdl, L.beams, (uint32_t)L.nchunk, 7u, (uint32_t)kUnitsBmf, L.ndf, L.early, part);
+  if (bmf && L.variant == 1) /* tuning point: 128-bit loads, 448 threads, 8 frames in flight */
+    return launch_k(b2p_fused_ldg128<Acc, BE, 8, false>, grid, dim3(448), 14 * 7 * sizeof(T), st,
+                    pdl, L.beams, (uint32_t)L.nchunk, 7u, (uint32_t)kUnitsBmf, L.ndf, L.early, part);
   if (bmf) {
-    b2p_fused_ldg_bmf<Acc, BE, kLdgUnroll><<<grid, kUnitsBmf, 0, st>>>(
-        L.beams, (uint32_t)L.nchunk, L.ndf, (T *)L.partials);
-  } else {
-    const int nt = 32 * L.nch;
-    const size_t sh = (size_t)(nt / 32) * L.nch * sizeof(T);
-    b2p_fused_ldg_any<Acc, BE><<<grid, nt, sh, st>>>(L.beams, (uint32_t)L.nchunk, (uint32_t)L.nch,
-                                                     (uint32_t)(L.nsamp * L.nch / 2), L.ndf,
-                                                     (T *)L.partials);
+    if (L.variant == 2)
+      return launch_k(b2p_fused_ldg256_bmf<Acc, BE, 2, 6>, grid, dim3(224), 0, st, pdl, L.beams,
+                      (uint32_t)L.nchunk, L.ndf, L.early, part);
+    if (L.variant == 3)
+      return launch_k(b2p_fused_ldg256_bmf<Acc, BE, 8, 2>, grid, dim3(224), 0, st, pdl, L.beams,
+                      (uint32_t)L.nchunk, L.ndf, L.early, part);
+    /* default: 4 x 256-bit loads in flight per thread, 4 CTAs/SM — fastest measured */
+    return launch_k(b2p_fused_ldg256_bmf<Acc, BE, 4, 4>, grid, dim3(224), 0, st, pdl, L.beams,
+                    (uint32_t)L.nchunk, L.ndf, L.early, part);
   }
-  return cudaGetLastError();
+  const int nt = 32 * L.nch;
+  const size_t sh = (size_t)(nt / 32) * L.nch * sizeof(T);
+  return launch_k(b2p_fused_ldg128<Acc, BE, 4, false>, grid, dim3(nt), sh, st, pdl, L.beams,
+                  (uint32_t)L.nchunk, (uint32_t)L.nch, (uint32_t)(L.nsamp * L.nch / 2), L.ndf,
+                  L.early, part);
 }
 
 template <typename Acc, bool BE, int G, int NSTAGE> cudaError_t configure_tma()
@@ -507,6 +660,19 @@ template <typename Acc, bool BE> cudaError_t configure_all()
   if ((e = configure_tma<Acc, BE, 4, kTmaStagesG4>()) != cudaSuccess) return e;
   if ((e = configure_tma<Acc, BE, 2, kTmaStagesG2>()) != cudaSuccess) return e;
   return configure_tma<Acc, BE, 1, kTmaStagesG1>();
+}
+
+template <typename T> cudaError_t launch_reduce_t(const B2pReduce &R, cudaStream_t st)
+{
+  const uint32_t nwarps = (uint32_t)R.nrows * (uint32_t)R.nchan;
+  const dim3 grid((nwarps * 32 + 255) / 256);
+  if (R.finish)
+    return launch_k(b2p_reduce_k<T, true>, grid, dim3(256), 0, st, R.pdl != 0, R.slots,
+                    (uint32_t)R.nrows, (uint32_t)R.nsplit, (uint32_t)R.nchan,
+                    (const T *)R.partials, (T *)R.acc, R.out, R.scale);
+  return launch_k(b2p_reduce_k<T, false>, grid, dim3(256), 0, st, R.pdl != 0, R.slots,
+                  (uint32_t)R.nrows, (uint32_t)R.nsplit, (uint32_t)R.nchan, (const T *)R.partials,
+                  (T *)R.acc, R.out, R.scale);
 }
 } /* namespace */
 
@@ -526,28 +692,10 @@ cudaError_t b2p_launch_fused(const B2pLaunch &L, cudaStream_t st)
   return L.big_endian ? launch_fused_t<AccExact, true>(L, st) : launch_fused_t<AccExact, false>(L, st);
 }
 
-cudaError_t b2p_launch_finalize(const B2pLaunch &L, cudaStream_t st)
+cudaError_t b2p_launch_reduce(const B2pReduce &R, cudaStream_t st)
 {
-  const uint32_t nchan = (uint32_t)(L.nchunk * L.nch);
-  dim3 grid((nchan + 127) / 128, (unsigned)L.nbeam);
-  if (L.mode == B2P_MODE_FLOAT)
-    b2p_finalize<double><<<grid, 128, 0, st>>>(L.beams, (uint32_t)L.nsplit, nchan,
-                                               (const double *)L.partials, (double *)L.acc);
-  else
-    b2p_finalize<unsigned long long><<<grid, 128, 0, st>>>(
-        L.beams, (uint32_t)L.nsplit, nchan, (const unsigned long long *)L.partials,
-        (unsigned long long *)L.acc);
-  return cudaGetLastError();
-}
-
-cudaError_t b2p_launch_finish(void *acc, float *out, int n, float scale, int mode, cudaStream_t st)
-{
-  const int grid = (n + 127) / 128;
-  if (mode == B2P_MODE_FLOAT)
-    b2p_finish_k<double><<<grid, 128, 0, st>>>((double *)acc, out, n, scale);
-  else
-    b2p_finish_k<unsigned long long><<<grid, 128, 0, st>>>((unsigned long long *)acc, out, n, scale);
-  return cudaGetLastError();
+  if (R.mode == B2P_MODE_FLOAT) return launch_reduce_t<double>(R, st);
+  return launch_reduce_t<unsigned long long>(R, st);
 }
 
 cudaError_t b2p_launch_synth(void *dptr, uint64_t ndf, int nchunk, int nch, int nsamp,

@@ -170,3 +170,61 @@ def test_bad_arguments_fail_loudly(b2p):
     with pytest.raises(b2p.B2pError):
         st.accumulate_device([8], 4)       # misaligned
     st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_chained_integrations_do_not_race(b2p, oracle_mod, kernel):
+    """Back-to-back integrations on the context's own stream: kernels are PDL-chained and a
+    fused kernel starts under the tail of its predecessor; every spectrum must still be exact."""
+    g = oracle_mod.Geometry()
+    nblk, ndf, nrun = 5, 300, 30
+    blocks = [oracle_mod.synth_fill(ndf, seed=500 + i, mode=i % 2) for i in range(nblk)]
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(b)) for b in blocks]
+    dev = [b2p.DeviceBuffer(b.nbytes) for b in blocks]
+    for d, b in zip(dev, blocks):
+        d.upload(b)
+    outs = b2p.DeviceBuffer(nrun * g.nchan * 4)
+    st = b2p.Baseband2Power(kernel=kernel)
+    for i in range(nrun):
+        st.accumulate_device([dev[i % nblk]], ndf)
+        st.finish_device(outs.ptr + i * g.nchan * 4)
+    b2p.device_sync(0)   # the context stream is non-blocking: a legacy-stream copy does not wait for it
+    got = outs.download().view(np.float32).reshape(nrun, g.nchan)
+    for i in range(nrun):
+        assert np.array_equal(got[i].view(np.uint32), want[i % nblk].view(np.uint32)), i
+    # two accumulates per integration as well (fold kernel between them)
+    for i in range(nrun):
+        st.accumulate_device([dev[i % nblk]], ndf)
+        st.accumulate_device([dev[(i + 1) % nblk]], ndf)
+        st.finish_device(outs.ptr + i * g.nchan * 4)
+    b2p.device_sync(0)
+    got = outs.download().view(np.float32).reshape(nrun, g.nchan)
+    for i in range(nrun):
+        s = oracle_mod.accumulate_omp(blocks[i % nblk]) + oracle_mod.accumulate_omp(blocks[(i + 1) % nblk])
+        assert np.array_equal(got[i].view(np.uint32), oracle_mod.finish(s).view(np.uint32)), i
+    st.close()
+    for d in dev:
+        d.free()
+    outs.free()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_caller_stream(b2p, oracle_mod, kernel):
+    """A caller-owned (torch) stream: producer kernel -> our kernels -> consumer on one stream."""
+    torch = pytest.importorskip("torch")
+    g = oracle_mod.Geometry()
+    ndf = 64
+    block = oracle_mod.synth_fill(ndf, seed=77, mode=1)
+    want = oracle_mod.finish(oracle_mod.accumulate_omp(block))
+    s = torch.cuda.Stream()
+    src = torch.from_numpy(block).cuda()
+    with torch.cuda.stream(s):
+        for _ in range(5):
+            buf = src.clone()                         # produced on the same stream right before
+            out = torch.empty(g.nchan, dtype=torch.float32, device="cuda")
+            st = b2p.Baseband2Power(kernel=kernel)
+            st.accumulate_device([buf], ndf, s.cuda_stream)
+            st.finish_device(out, s.cuda_stream)
+            res = out.cpu().numpy()
+            assert np.array_equal(res.view(np.uint32), want.view(np.uint32))
+            st.close()

@@ -13,6 +13,7 @@ ap.add_argument("--ndf", type=int, default=8192)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--kernels", default="ldg,tma")
 ap.add_argument("--nsplits", default="0")
+ap.add_argument("--variants", default="0")
 args = ap.parse_args()
 
 print(json.dumps(device_info(0)))
@@ -24,6 +25,8 @@ for b in range(nb):
 ptrs = [buf.ptr + b * per for b in range(nb)]
 out = DeviceBuffer(nb * BMF.nchan * 4)
 for kernel in args.kernels.split(","):
+  for variant in args.variants.split(","):
+    os.environ["B2P_VARIANT"] = variant
     for ns in [int(x) for x in args.nsplits.split(",")]:
         st = Baseband2Power(kernel=kernel, nbeam=nb, nsplit=ns)
         for _ in range(3):
@@ -36,11 +39,15 @@ for kernel in args.kernels.split(","):
             st.finish_device(out)
             ms, n = st.fused_time_ms()
             times.append(ms / n)
+        got = out.download().tobytes()
+        if "ref_out" not in globals():
+            ref_out = got
+        match = got == ref_out
         times.sort()
         best, med = times[0], times[len(times) // 2]
         gb = nb * per / 1e9
-        print(json.dumps({"kernel": kernel, "nsplit": st.nsplit, "nbeam": nb, "ndf": ndf,
-                          "best_ms": round(best, 4), "median_ms": round(med, 4),
+        print(json.dumps({"kernel": kernel, "variant": variant, "nsplit": st.nsplit, "nbeam": nb, "ndf": ndf,
+                          "match": match, "best_ms": round(best, 4), "median_ms": round(med, 4),
                           "best_GBps": round(gb / best * 1e3, 1), "median_GBps": round(gb / med * 1e3, 1)}),
               flush=True)
         st.close()
