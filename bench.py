@@ -214,9 +214,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    host_pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_pg = dist.new_group(backend="gloo")   # spectra are gathered host-side, 1344 B per beam
 
     def barrier():
         if world > 1:
@@ -298,15 +300,38 @@ def main():
             for b in range(nbeam):
                 rc = lib.b2p_memcpy_d2h(local, pinned[r][b].ptr, dev_in.data_ptr() + (r * nbeam + b) * blk, blk)
                 assert rc == 0
+        from paf_baseband2power_b200.sharding import gather_spectra
+        my_beams = list(range(rank * nbeam, (rank + 1) * nbeam))
         ste = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel)
-        for i in range(3):
+
+        def e2e_step(i):
             ste.accumulate_host(pinned[i % hrot], ndf)
-            spec = ste.finish()
+            sp = ste.finish()                       # D2H of the spectra inside the timed region
+            if world > 1:                           # the only cross-rank traffic of the path
+                allsp = gather_spectra(sp, [b // 1 for b in range(rank, world * nbeam, world)][:nbeam],
+                                       world * nbeam, group=host_pg)
+                return sp, allsp
+            return sp, sp
+
+        for i in range(3):
+            spec, _ = e2e_step(i)
+        # plain pinned H2D of one block: the link ceiling the e2e number sits under
+        link0, link1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_t = torch.empty(blk, dtype=torch.uint8, device="cuda")
+        hsrc = torch.from_numpy(pinned[0][0].array)
+        stage_t.copy_(hsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        link0.record()
+        for _ in range(3):
+            stage_t.copy_(hsrc, non_blocking=True)
+        link1.record()
+        torch.cuda.synchronize()
+        h2d_link = 3 * blk / (link0.elapsed_time(link1) * 1e-3) / 1e9
+        del stage_t
         barrier()
         t0 = time.perf_counter()
         for i in range(ke):
-            ste.accumulate_host(pinned[i % hrot], ndf)
-            spec = ste.finish()
+            spec, _ = e2e_step(i)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
@@ -315,7 +340,10 @@ def main():
                "h2d_bytes_per_step": nbeam * blk, "d2h_bytes_per_step": nbeam * g.out_bytes,
                "ms_per_step": round(e2e_ms, 3), "steps": ke,
                "realtime_factor": round(world * nbeam * g.t_integration_s * ndf / 8192 / (e2e_ms * 1e-3), 2),
-               "path": "b2p_accumulate_host (pinned ring block, 256-frame pieces, 3 staging buffers) + b2p_finish"}
+               "h2d_link_GBps_per_gpu": round(h2d_link, 2),
+               "frac_of_h2d_link": round(nbeam * blk / (e2e_ms * 1e-3) / 1e9 / h2d_link, 4),
+               "path": "b2p_accumulate_host (pinned ring block, 256-frame pieces, 3 staging buffers) + b2p_finish"
+                       + (" + gloo gather of spectra to rank 0" if world > 1 else "")}
         e2e_last = spec[0].copy()
         ste.close()
     clocks = sampler.stop()

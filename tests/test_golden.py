@@ -1,0 +1,110 @@
+"""Oracle and shipped artefacts against the committed golden fixtures (tests/golden, made by
+tools/make_golden.py).  reference_artifacts.json and bmf_hdr_vectors.json come from the
+reference itself; oracle_vectors.json pins the oracle against regressions (PARITY UNPINNED)."""
+import configparser
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import b2p_oracle_np as onp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CONF = os.path.join(ROOT, "paf_baseband2power_b200", "conf")
+
+
+def _load(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+def test_header_template_matches_reference_key_for_key():
+    ref = _load("reference_artifacts.json")["header_kv"]
+    got = []
+    for line in open(os.path.join(CONF, "header_baseband2power.txt")):
+        line = line.split("#")[0].strip()
+        if line:
+            p = line.split(None, 1)
+            got.append([p[0], p[1].strip() if len(p) > 1 else ""])
+    assert got == ref
+    assert os.path.getsize(os.path.join(CONF, "header_baseband2power.txt")) < 4096
+
+
+def test_conf_matches_reference_key_for_key():
+    ref = _load("reference_artifacts.json")["conf"]
+    c = configparser.ConfigParser()
+    c.read(os.path.join(CONF, "paf-baseband2power.conf"))
+    assert {s: dict(c[s]) for s in c.sections()} == ref
+
+
+def test_geometry_follows_conf():
+    from paf_baseband2power_b200 import BMF
+    ref = _load("reference_artifacts.json")["conf"]
+    assert BMF.nsamp_df == int(ref["BasicConf"]["nsamp_df"])
+    assert BMF.nchunk == int(ref["BasicConf"]["nchk_nic"])
+    assert BMF.ndf == int(ref["DiskdbConf"]["ndf"])
+    assert BMF.nchan == int(ref["Baseband2powerConf"]["nchan"])
+    assert BMF.block_bytes == 8192 * 48 * 7168 == 2818572288      # paf-baseband2power.py:67
+    assert BMF.out_bytes == 336 * 4 == 1344                        # paf-baseband2power.py:79
+    assert abs(BMF.t_integration_s - 0.884736) < 1e-12             # README.md:2
+
+
+@pytest.mark.parametrize("impl", ["c", "numpy"])
+def test_oracle_vectors(oracle_mod, impl):
+    gold = _load("oracle_vectors.json")
+    for case in gold["cases"]:
+        if impl == "c":
+            blk = oracle_mod.synth_fill(case["ndf"], case["seed"], case["first_word"], case["mode"])
+            sums = oracle_mod.accumulate(blk)
+            f1, fm = oracle_mod.finish(sums, 1.0), oracle_mod.finish(sums, 2.0 ** -20)
+        else:
+            blk = onp.synth_block(case["ndf"], case["seed"], case["first_word"], case["mode"])
+            sums = onp.channel_sums(blk)
+            f1, fm = onp.finish(sums, 1.0), onp.finish(sums, 2.0 ** -20)
+        assert hashlib.sha256(blk.tobytes()).hexdigest() == case["sha256"]
+        assert [str(int(x)) for x in sums] == case["sums"]
+        assert [int(x) for x in f1.view(np.uint32)] == case["f32_sum_bits"]
+        assert [int(x) for x in fm.view(np.uint32)] == case["f32_mean_bits"]
+
+
+def test_tiny_block_pure_python_sums(oracle_mod):
+    t = _load("tiny_block.json")
+    raw = np.frombuffer(bytes.fromhex(t["raw_hex"]), dtype=np.uint8)
+    g = oracle_mod.Geometry(nchunk=t["nchunk"], nch_per_chunk=t["nch_per_chunk"], nsamp_df=t["nsamp_df"])
+    want = [int(s) for s in t["sums"]]
+    assert [int(x) for x in oracle_mod.accumulate(raw, g=g)] == want
+    assert [int(x) for x in onp.channel_sums(raw, nchunk=g.nchunk, nch=g.nch_per_chunk, nsamp=g.nsamp_df)] == want
+
+
+@pytest.mark.gpu
+def test_gpu_against_golden(b2p):
+    """The CUDA path against the committed vectors (no oracle code involved at run time
+    except the host generator's bytes, whose sha256 is checked first)."""
+    import oracle
+    gold = _load("oracle_vectors.json")
+    for kernel in ("ldg", "tma"):
+        for case in gold["cases"]:
+            dev = b2p.DeviceBuffer(case["ndf"] * 48 * 7168)
+            dev.synth_fill(case["ndf"], case["seed"], case["first_word"], case["mode"])
+            assert hashlib.sha256(dev.download().tobytes()).hexdigest() == case["sha256"]
+            st = b2p.Baseband2Power(kernel=kernel)
+            st.accumulate_device([dev], case["ndf"])
+            assert [str(int(x)) for x in st.read_sums()[0]] == case["sums"]
+            assert [int(x) for x in st.finish()[0].view(np.uint32)] == case["f32_sum_bits"]
+            st.close()
+            st = b2p.Baseband2Power(kernel=kernel, scale=2.0 ** -20)
+            st.accumulate_device([dev], case["ndf"])
+            assert [int(x) for x in st.finish()[0].view(np.uint32)] == case["f32_mean_bits"]
+            st.close()
+            dev.free()
+    t = _load("tiny_block.json")
+    raw = np.frombuffer(bytes.fromhex(t["raw_hex"]), dtype=np.uint8)
+    st = b2p.Baseband2Power(nchunk=t["nchunk"], nch_per_chunk=t["nch_per_chunk"], nsamp_df=t["nsamp_df"])
+    dev = b2p.DeviceBuffer(raw.nbytes)
+    dev.upload(raw)
+    st.accumulate_device([dev], t["ndf"])
+    assert [str(int(x)) for x in st.read_sums()[0]] == t["sums"]
+    st.close()
+    dev.free()
