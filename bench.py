@@ -139,21 +139,21 @@ def run_reference(args, rank, world):
     gc = g.c()
     import ctypes
     L.b2p_oracle_synth_fill(block.ctypes.data, ndf, ctypes.byref(gc), 1, 0, 1)
-    threads = L.b2p_oracle_max_threads()
+    threads = _host_threads()   # explicit: torchrun exports OMP_NUM_THREADS=1
     sums = np.zeros(g.nchan, dtype=np.uint64)
     for _ in range(args.warmup):
-        oracle.accumulate_omp(block, ndf, g, sums=sums, L=L)
+        oracle.accumulate_omp(block, ndf, g, sums=sums, nthreads=threads, L=L)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         sums[:] = 0
-        oracle.accumulate_omp(block, ndf, g, sums=sums, L=L)
+        oracle.accumulate_omp(block, ndf, g, sums=sums, nthreads=threads, L=L)
         oracle.finish(sums, 1.0)
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
     gbs = block.nbytes / (ms * 1e-3) / 1e9
     t_int = ndf * 128 * 27.0 / 32.0 * 1e-6
     sample = f"{args.steps} steps x 1 beam-integration of {ndf} frames ({block.nbytes} B) on host RAM"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
@@ -164,7 +164,7 @@ def run_reference(args, rank, world):
                          "sample": sample,
                          "note": "reference kernel absent (kernel.cu:1-7): C port of the specification, gcc -O3 -march=native -fopenmp"},
         "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }))
 
 
 def _config(args, nbeam):
@@ -178,6 +178,35 @@ def _config(args, nbeam):
         "l2": "inputs larger than L2: 4 rotating 2.8 GB blocks per beam (value), 2 rotating pinned blocks (e2e)",
         "parallelism": f"beams sharded by rank, {args.gpus} x independent, no collective on the data path",
     }
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Only the one JSON line may reach stdout: libraries (NCCL prints its version there)
+    are pointed at stderr for the run; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def main():
@@ -200,6 +229,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    _guard_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -300,16 +330,15 @@ def main():
             for b in range(nbeam):
                 rc = lib.b2p_memcpy_d2h(local, pinned[r][b].ptr, dev_in.data_ptr() + (r * nbeam + b) * blk, blk)
                 assert rc == 0
-        from paf_baseband2power_b200.sharding import gather_spectra
-        my_beams = list(range(rank * nbeam, (rank + 1) * nbeam))
+        from paf_baseband2power_b200.sharding import beams_for_rank, gather_spectra
+        my_beams = beams_for_rank(world * nbeam, rank, world)
         ste = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel)
 
         def e2e_step(i):
             ste.accumulate_host(pinned[i % hrot], ndf)
             sp = ste.finish()                       # D2H of the spectra inside the timed region
             if world > 1:                           # the only cross-rank traffic of the path
-                allsp = gather_spectra(sp, [b // 1 for b in range(rank, world * nbeam, world)][:nbeam],
-                                       world * nbeam, group=host_pg)
+                allsp = gather_spectra(sp, my_beams, world * nbeam, group=host_pg)
                 return sp, allsp
             return sp, sp
 
@@ -361,13 +390,13 @@ def main():
         else:
             host = pinned[(ke - 1) % hrot][0].array
             check_against = e2e_last
-        threads = L.b2p_oracle_max_threads()
+        threads = _host_threads()
         times = []
         t_begin = time.perf_counter()
         while True:
             sums = np.zeros(og.nchan, dtype=np.uint64)
             t0 = time.perf_counter()
-            oracle.accumulate_omp(host, ndf, og, sums=sums, L=L)
+            oracle.accumulate_omp(host, ndf, og, sums=sums, nthreads=threads, L=L)
             times.append(time.perf_counter() - t0)
             if time.perf_counter() - t_begin > 10.0 or len(times) >= 200:
                 break
@@ -431,7 +460,7 @@ def main():
                 "achieved_in_stream": round(alg_bytes / (ms_step * 1e-3) / 1e9, 1),
                 "frac_of_nominal_8000": round(achieved / 8000.0, 4)}
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
@@ -441,7 +470,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "parity_vs_oracle": parity,
             "beamset": beamset, "device": device_info(local)["name"],
-        }), flush=True)
+        }))
     st.close()
     if world > 1:
         dist.destroy_process_group()
