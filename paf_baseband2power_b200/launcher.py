@@ -1,0 +1,213 @@
+#!/usr/bin/env python3
+"""Pipeline launcher — a working Python-3 restatement of paf-baseband2power.py.
+
+The reference launcher cannot run (Python 2, a syntax error at
+paf-baseband2power.py:90,92, undefined args.psrname/args.dfname at :37-38).
+What it set out to do is kept: read paf-baseband2power.conf (:49-80), size the
+two rings (input NDF*NCHK_NIC*7168 :67, output NCHAN*NBYTE :79), write the key
+files (:101-112), create the rings (`dada_db -l -p -k -b -n -r`, :114-115), run
+paf_diskdb, paf_baseband2power and the ring-to-disk writer pinned to cores 0, 1,
+2 (:68,80,83,85-95), wait for the three, destroy the rings (:129-130).
+
+Same flags (-a conf, -b directory, -c gpu, -d visible gpu, -e memcheck) plus the
+data-file name the reference forgot to declare (-f).  Multi-beam: --beams N runs
+N independent pipelines (own ring keys per beam, beam b on GPU gpus[b % len]) —
+the sharding of DESIGN.md §7; no process talks to another beam's process.
+"""
+from __future__ import annotations
+
+import argparse
+import configparser
+import os
+import shutil
+import subprocess
+import sys
+import threading
+from dataclasses import dataclass, field
+from typing import List
+
+from .sharding import ring_keys_for_beam
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(PKG, "bin")
+PKT_BYTES = 7168  # DT_SIZE, capture.h:28 — the literal the reference launcher uses (:67)
+
+
+@dataclass
+class PipelineConf:
+    nsamp_df: int
+    npol_samp: int
+    ndim_pol: int
+    nchk_nic: int
+    diskdb_ndf: int
+    diskdb_nbuf: int
+    diskdb_key: int
+    diskdb_kfname: str
+    diskdb_hfname: str
+    diskdb_nreader: int
+    diskdb_sod: int
+    b2p_key: int
+    b2p_kfname: str
+    b2p_nreader: int
+    b2p_sod: int
+    b2p_nbuf: int
+    b2p_nchan: int
+    b2p_nbyte: int
+
+    @property
+    def diskdb_rbufsz(self) -> int:
+        return self.diskdb_ndf * self.nchk_nic * PKT_BYTES
+
+    @property
+    def b2p_rbufsz(self) -> int:
+        return self.b2p_nchan * self.b2p_nbyte
+
+
+def read_conf(path: str) -> PipelineConf:
+    cp = configparser.ConfigParser()
+    if not cp.read(path):
+        raise FileNotFoundError(path)
+    b, d, p = cp["BasicConf"], cp["DiskdbConf"], cp["Baseband2powerConf"]
+    return PipelineConf(
+        nsamp_df=int(b["nsamp_df"]), npol_samp=int(b["npol_samp"]), ndim_pol=int(b["ndim_pol"]),
+        nchk_nic=int(b["nchk_nic"]),
+        diskdb_ndf=int(d["ndf"]), diskdb_nbuf=int(d["nblk"]), diskdb_key=int(d["key"], 16),
+        diskdb_kfname=d["kfname_prefix"] + ".key", diskdb_hfname=d["hfname"],
+        diskdb_nreader=int(d["nreader"]), diskdb_sod=int(d["sod"]),
+        b2p_key=int(p["key"], 16), b2p_kfname=p["kfname_prefix"] + ".key",
+        b2p_nreader=int(p["nreader"]), b2p_sod=int(p["sod"]), b2p_nbuf=int(p["nblk"]),
+        b2p_nchan=int(p["nchan"]), b2p_nbyte=int(p["nbyte"]))
+
+
+@dataclass
+class BeamPlan:
+    beam: int
+    gpu: int
+    key_in: int
+    key_out: int
+    create: List[List[str]] = field(default_factory=list)
+    stages: List[List[str]] = field(default_factory=list)
+    destroy: List[List[str]] = field(default_factory=list)
+
+
+def _pin(cmd: List[str], cpu: int | None) -> List[str]:
+    if cpu is None or shutil.which("taskset") is None or cpu >= (os.cpu_count() or 1):
+        return cmd
+    return ["taskset", "-c", str(cpu)] + cmd
+
+
+def plan(conf: PipelineConf, directory: str, dfnames: List[str], gpus: List[int], memcheck: bool = False,
+         hfname: str | None = None, extra_stage_args: List[str] | None = None, pin: bool = True) -> List[BeamPlan]:
+    """The exact commands for every beam; nothing is executed here."""
+    plans = []
+    hf = hfname or conf.diskdb_hfname
+    if not os.path.isabs(hf):
+        cand = os.path.join(directory, hf)
+        hf = cand if os.path.exists(cand) else os.path.join(PKG, "conf", os.path.basename(hf))
+    for beam, dfname in enumerate(dfnames):
+        if len(dfnames) == 1:
+            kin, kout = conf.diskdb_key, conf.b2p_key
+        else:
+            kin, kout = ring_keys_for_beam(beam, conf.diskdb_key, conf.b2p_key)
+        gpu = gpus[beam % len(gpus)]
+        bp = BeamPlan(beam, gpu, kin, kout)
+        db = os.path.join(BIN, "paf_dada_db")
+        bp.create = [
+            [db, "-l", "-p", "-k", f"{kin:x}", "-b", str(conf.diskdb_rbufsz), "-n", str(conf.diskdb_nbuf), "-r", str(conf.diskdb_nreader)],
+            [db, "-l", "-p", "-k", f"{kout:x}", "-b", str(conf.b2p_rbufsz), "-n", str(conf.b2p_nbuf), "-r", str(conf.b2p_nreader)],
+        ]
+        bp.destroy = [[db, "-d", "-k", f"{kin:x}"], [db, "-d", "-k", f"{kout:x}"]]
+        cpu0 = 3 * beam if pin else None
+        stage = [os.path.join(BIN, "paf_baseband2power"), "-a", f"{kin:x}", "-b", f"{kout:x}", "-c", directory, "-d", str(gpu)]
+        stage += extra_stage_args or []
+        if memcheck:  # the reference wrapped the stage in cuda-memcheck (:89-90); its successor:
+            stage = ["compute-sanitizer", "--tool", "memcheck"] + stage
+        out_name = f"beam{beam:02d}_spectra.dada"
+        bp.stages = [
+            _pin([os.path.join(BIN, "paf_diskdb"), "-a", f"{kin:x}", "-b", directory, "-c", dfname, "-d", hf, "-e", str(conf.diskdb_sod)], cpu0),
+            _pin(stage, None if cpu0 is None else cpu0 + 1),
+            _pin([os.path.join(BIN, "paf_dbdisk"), "-k", f"{kout:x}", "-D", directory, "-f", out_name, "-W"], None if cpu0 is None else cpu0 + 2),
+        ]
+        plans.append(bp)
+    return plans
+
+
+def write_key_files(conf: PipelineConf, directory: str, plans: List[BeamPlan]):
+    for bp in plans:
+        suffix = "" if len(plans) == 1 else f".beam{bp.beam:02d}"
+        for fname, key in ((conf.diskdb_kfname, bp.key_in), (conf.b2p_kfname, bp.key_out)):
+            with open(os.path.join(directory, fname + suffix), "w") as f:
+                f.write("DADA INFO:\n")
+                f.write(f"key {key:x}\n")
+
+
+def run(plans: List[BeamPlan], timeout: float | None = None) -> int:
+    """Create rings, run the three stages of every beam concurrently, destroy rings."""
+    rc = 0
+    created: List[BeamPlan] = []
+    try:
+        for bp in plans:
+            for cmd in bp.create:
+                subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+            created.append(bp)
+        procs, results = [], {}
+
+        def wait(i, p):
+            try:
+                results[i] = p.wait(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                results[i] = -9
+
+        for bp in plans:
+            # consumer first, producer last: nobody blocks on a ring without a reader
+            for cmd in (bp.stages[2], bp.stages[1], bp.stages[0]):
+                procs.append(subprocess.Popen(cmd))
+        threads = [threading.Thread(target=wait, args=(i, p)) for i, p in enumerate(procs)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        rc = max((abs(v) for v in results.values()), default=0)
+    finally:
+        for bp in created:
+            for cmd in bp.destroy:
+                subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return rc
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description="Detect PAF BMF baseband from DADA files and integrate it (B200)")
+    ap.add_argument("-a", "--cfname", required=True, help="The name of configuration file")
+    ap.add_argument("-b", "--directory", required=True, help="Directory with the data files; spectra and logs are written there")
+    ap.add_argument("-c", "--gpu", type=int, nargs="+", default=[0], help="The index of GPU (several: beams round-robin)")
+    ap.add_argument("-d", "--visiblegpu", default="", help="Visible GPU(s) inside a container; sets CUDA_VISIBLE_DEVICES unless '' or 'all'")
+    ap.add_argument("-e", "--memcheck", type=int, default=0, help="Run the stage under compute-sanitizer memcheck")
+    ap.add_argument("-f", "--dfname", nargs="+", required=True, help="DADA data file name(s), one per beam")
+    ap.add_argument("--ndf", type=int, default=0, help="override NDF (frames per ring block) of the conf")
+    ap.add_argument("--nblk", type=int, default=0, help="override NBLK (input ring blocks) of the conf")
+    ap.add_argument("--average", type=int, default=0, help="1: time average instead of integral")
+    ap.add_argument("--dry-run", action="store_true", help="print the commands, run nothing")
+    ap.add_argument("--timeout", type=float, default=None)
+    args = ap.parse_args(argv)
+
+    conf = read_conf(args.cfname)
+    if args.ndf:
+        conf.diskdb_ndf = args.ndf
+    if args.nblk:
+        conf.diskdb_nbuf = args.nblk
+    if args.visiblegpu not in ("", "all"):
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.visiblegpu
+    extra = ["-s", "1"] if args.average else []
+    plans = plan(conf, args.directory, args.dfname, args.gpu, bool(args.memcheck), extra_stage_args=extra)
+    if args.dry_run:
+        for bp in plans:
+            for cmd in bp.create + bp.stages + bp.destroy:
+                print(" ".join(cmd))
+        return 0
+    write_key_files(conf, args.directory, plans)
+    return run(plans, args.timeout)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
