@@ -263,6 +263,18 @@ char *ipcbuf_get_next_write(ipcbuf_t *id)
   return p;
 }
 
+char *ipcbuf_get_write_ahead(ipcbuf_t *id, unsigned ahead)
+{
+  if (!id || !id->sync || !id->is_writer) return NULL;
+  ipcsync_t *s = id->sync;
+  if ((uint64_t)ahead + 1 > s->nbufs) return NULL;
+  lock(s);
+  while (s->w_count + ahead - s->r_count >= s->nbufs) pthread_cond_wait(&s->cv, &s->mtx);
+  char *p = id->buffer[(s->w_count + ahead) % s->nbufs];
+  unlock(s);
+  return p;
+}
+
 int ipcbuf_mark_filled(ipcbuf_t *id, uint64_t nbytes)
 {
   if (!id || !id->sync || !id->is_writer) return -1;

@@ -74,6 +74,11 @@ int ipcbuf_eod(ipcbuf_t *id); /* reader: 1 once every valid buffer has been clea
 int ipcbuf_reset(ipcbuf_t *id); /* writer: forget a finished observation */
 
 char *ipcbuf_get_next_write(ipcbuf_t *id);
+/* Shim extension: the buffer `ahead` places after the next one to fill (0 = same as
+   ipcbuf_get_next_write); waits until the reader has freed it.  Lets the capture stage keep
+   two blocks open so late packets of block k and early ones of k+1 both land in the ring
+   (the reference spills into a malloc'ed side buffer and copies, capture.c:527-533). */
+char *ipcbuf_get_write_ahead(ipcbuf_t *id, unsigned ahead);
 int ipcbuf_mark_filled(ipcbuf_t *id, uint64_t nbytes);
 char *ipcbuf_get_next_read(ipcbuf_t *id, uint64_t *bytes);
 int ipcbuf_mark_cleared(ipcbuf_t *id);
