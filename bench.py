@@ -175,7 +175,7 @@ def _config(args, nbeam):
                      f"BASELINE.json configs[2]: {nbeam} beams batched per step, each 1 ring block of 2818572288 B"),
         "nbeam_per_gpu": nbeam, "ndf": args.ndf, "nchunk": 48, "nch_per_chunk": 7, "nsamp_df": 128,
         "mode": "exact-uint64", "kernel": args.kernel,
-        "l2": "inputs larger than L2: 4 rotating 2.8 GB blocks per beam (value), 2 rotating pinned blocks (e2e)",
+        "l2": "inputs larger than L2: up to 4 rotating 2.8 GB blocks per beam (value), 2 rotating pinned blocks (e2e)",
         "parallelism": f"beams sharded by rank, {args.gpus} x independent, no collective on the data path",
     }
 
@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--nbeam", type=int, default=1, help="beam streams per GPU per step")
     ap.add_argument("--ndf", type=int, default=8192, help="data frames per ring block")
     ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--nsplit", type=int, default=0, help="time splits per chunk (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 32)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -265,7 +266,9 @@ def main():
     nbeam, ndf = args.nbeam, args.ndf
     g = BMF
     blk = ndf * g.frame_bytes
-    nrot = 4
+    # rotate between distinct blocks so that no step can find its input in L2 (126 MB); one
+    # set is already 22x L2 per beam, so fewer sets are used when many beams fill the HBM
+    nrot = max(1, min(4, int(0.45 * torch.cuda.get_device_properties(local).total_memory // (nbeam * blk))))
     # ---- device-resident inputs: nrot distinct blocks per beam ----
     dev_in = torch.empty(nrot * nbeam * blk, dtype=torch.uint8, device="cuda")
     from paf_baseband2power_b200 import _lib
@@ -278,7 +281,7 @@ def main():
                                            1000 + beam_id, r * wpb, 1, None)
             assert rc == 0
     out_dev = torch.empty(nbeam * g.nchan, dtype=torch.float32, device="cuda")
-    st = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel)
+    st = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel, nsplit=args.nsplit)
     # The kernels run on the context's own stream (stream=None through the C ABI): only
     # there may a fused kernel start under the tail of its predecessor (PDL).  torch wraps
     # that same stream so the torch.cuda.Event pair below is recorded on it.

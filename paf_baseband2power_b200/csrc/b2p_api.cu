@@ -20,6 +20,7 @@
 #include "b2p_kernels.cuh"
 
 #define B2P_MAX_STAGE_BUFS 8
+#define B2P_NTICKETS 4096
 
 struct b2p_ctx {
   b2p_params p;
@@ -36,6 +37,10 @@ struct b2p_ctx {
   void *partials;
   float *out_dev;
   float *out_pinned;
+  /* ticket counters of the persistent (TMA) kernel: one zeroed counter per launch,
+     re-zeroed half a ring at a time, far away from the ones in use */
+  unsigned int *tickets;
+  uint64_t fused_seq;
   /* host-path staging */
   int nbufs;
   void *stage[B2P_MAX_STAGE_BUFS];
@@ -154,7 +159,7 @@ static int resolve_nsplit(const b2p_params *p, int kernel, int sm_count)
   if (kernel == B2P_KERNEL_TMA) {
     slots = (unsigned)sm_count;
     units = (unsigned)(p->nchunk / b2p_tma_group(p->nchunk)) * (unsigned)p->nbeam;
-    target = 37;
+    target = 222; /* items are drawn dynamically: many small ones balance the SMs */
   } else {
     slots = 4u * (unsigned)sm_count;
     units = (unsigned)p->nchunk * (unsigned)p->nbeam;
@@ -212,6 +217,8 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   c->nbufs = 0;
   c->acc = c->partials = NULL;
   c->out_dev = c->out_pinned = NULL;
+  c->tickets = NULL;
+  c->fused_seq = 0;
   c->compute = c->copy = NULL;
   for (int i = 0; i < B2P_MAX_STAGE_BUFS; ++i) {
     c->stage[i] = NULL;
@@ -242,6 +249,8 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(cudaMemset(c->acc, 0, nacc * c->acc_elem));
   CKC(cudaMalloc(&c->partials, nacc * (size_t)c->nsplit * c->acc_elem));
   CKC(cudaMalloc((void **)&c->out_dev, nacc * sizeof(float)));
+  CKC(cudaMalloc((void **)&c->tickets, B2P_NTICKETS * sizeof(unsigned int)));
+  CKC(cudaMemset(c->tickets, 0, B2P_NTICKETS * sizeof(unsigned int)));
   CKC(cudaHostAlloc((void **)&c->out_pinned, nacc * sizeof(float), cudaHostAllocDefault));
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -264,6 +273,7 @@ void b2p_destroy(b2p_ctx *c)
   if (c->acc) cudaFree(c->acc);
   if (c->partials) cudaFree(c->partials);
   if (c->out_dev) cudaFree(c->out_dev);
+  if (c->tickets) cudaFree(c->tickets);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->copy) cudaStreamDestroy(c->copy);
@@ -349,6 +359,16 @@ static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, i
   if (ns < 1) ns = 1;
   if (ns > (uint64_t)c->nsplit) ns = (uint64_t)c->nsplit;
   L.nsplit = (int)ns;
+
+  /* a fresh ticket counter per launch; when half the ring has been used, re-zero the
+     other half's predecessor block (stream-ordered, 2048 launches away from any use) */
+  const uint64_t seq = c->fused_seq++;
+  L.ticket = c->tickets + (seq % B2P_NTICKETS);
+  if (seq && seq % (B2P_NTICKETS / 2) == 0) {
+    const size_t half = (size_t)(((seq / (B2P_NTICKETS / 2)) + 1) % 2) * (B2P_NTICKETS / 2);
+    if (st != c->compute) CK(c, cudaStreamSynchronize(c->compute));
+    CK(c, cudaMemsetAsync(c->tickets + half, 0, (B2P_NTICKETS / 2) * sizeof(unsigned int), st));
+  }
 
   cudaEvent_t e0 = NULL, e1 = NULL;
   if (c->timing) {

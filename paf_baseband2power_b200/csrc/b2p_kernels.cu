@@ -377,29 +377,39 @@ __device__ __forceinline__ void consumer_bar()
 
 /* ------------------------------------------------ TMA kernel, BMF geometry */
 /*
- * Work item = (beam, time split, chunk group of G).  Item i belongs to CTA
- * i % gridDim.x.  One stage = the G packets of one data frame of the group:
- * G*7168 contiguous bytes.  Consumer thread j reads unit j of each packet, so
- * it keeps 2 accumulators per packet slot g.
+ * Work item = (beam, time split, chunk group of G).  Persistent CTAs (one per SM)
+ * draw items from a ticket counter, so SMs that stream faster (nearer L2 slices)
+ * simply take more items and all of them finish together — with a static
+ * round-robin ncu showed SMs only 89 % active (a long tail).  One stage = the G
+ * packets of one data frame of the group: G*7168 contiguous bytes, one bulk
+ * copy.  The producer tags every stage with its item (and whether it is the
+ * item's last frame); the consumers just follow the tags, so they never need
+ * the schedule.  Consumer thread j reads unit j of each packet: 2 accumulators
+ * per packet slot g.
  */
 template <int G, int NSTAGE> struct TmaSmem {
   static constexpr int kStageBytes = G * kPktBytes;
   static constexpr int kBarOff = NSTAGE * kStageBytes;
-  static constexpr int kRedOff = kBarOff + 2 * NSTAGE * 8;
+  static constexpr int kTagOff = kBarOff + 2 * NSTAGE * 8;
+  static constexpr int kRedOff = kTagOff + NSTAGE * 8;
   static constexpr int kBytes = kRedOff + kTmaConsumerWarps * G * kNchBmf * 8;
 };
 
-template <typename Acc, bool BE, int G, int NSTAGE>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+constexpr uint32_t kTagLast = 0x80000000u; /* last frame of the item */
+constexpr uint32_t kTagEnd = 0xFFFFFFFFu;  /* no more work for this CTA */
+
+template <typename Acc, bool BE, int G, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(kTmaThreads, MINB)
 b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t ndf,
                   const uint32_t nsplit, const uint32_t nitems, const int early,
-                  typename Acc::type *__restrict__ partials)
+                  unsigned int *__restrict__ ticket, typename Acc::type *__restrict__ partials)
 {
   typedef typename Acc::type T;
   typedef TmaSmem<G, NSTAGE> S;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = (uint64_t *)(smem + S::kBarOff);
   uint64_t *empty = full + NSTAGE;
+  volatile uint32_t *tag = (volatile uint32_t *)(smem + S::kTagOff);
   T *red = (T *)(smem + S::kRedOff);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -416,45 +426,60 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
   __syncthreads();
 
   if (warp == kTmaConsumerWarps) {
-    /* ---- producer: one lane issues every bulk copy of this CTA ---- */
+    /* ---- producer: one lane draws tickets and issues every bulk copy of this CTA ---- */
     if (lane == 0) {
       uint32_t it = 0;
-      for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const uint32_t group = item % ngroups, rest = item / ngroups;
-        const uint32_t split = rest % nsplit, beam = rest / nsplit;
-        uint64_t f0, f1;
-        split_range(ndf, split, nsplit, f0, f1);
-        const unsigned char *src = (const unsigned char *)beams.ptr[beam] +
-                                   (f0 * nchunk + (uint64_t)group * G) * kPktBytes;
+      for (;;) {
+        const uint32_t item = atomicAdd(ticket, 1u);
+        const bool end = item >= nitems;
+        uint64_t f0 = 0, f1 = 1;
+        const unsigned char *src = nullptr;
+        if (!end) {
+          const uint32_t group = item % ngroups, rest = item / ngroups;
+          const uint32_t split = rest % nsplit, beam = rest / nsplit;
+          split_range(ndf, split, nsplit, f0, f1);
+          src = (const unsigned char *)beams.ptr[beam] + (f0 * nchunk + (uint64_t)group * G) * kPktBytes;
+          if (f1 == f0) { /* an empty split still owes its (zero) partial sums */
+            const uint32_t s = it % NSTAGE, k = it / NSTAGE;
+            if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+            tag[s] = item | kTagLast | 0x40000000u; /* bit 30: no data in this stage */
+            mbar_arrive(&full[s]);
+            ++it;
+            continue;
+          }
+        }
         const size_t fstride = (size_t)nchunk * kPktBytes;
         for (uint64_t f = f0; f < f1; ++f, ++it, src += fstride) {
           const uint32_t s = it % NSTAGE, k = it / NSTAGE;
           if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], S::kStageBytes);
-          bulk_g2s(smem + s * S::kStageBytes, src, S::kStageBytes, &full[s]);
+          if (end) {
+            tag[s] = kTagEnd;
+            mbar_arrive(&full[s]);
+          } else {
+            tag[s] = item | (f + 1 == f1 ? kTagLast : 0u);
+            mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+            bulk_g2s(smem + s * S::kStageBytes, src, S::kStageBytes, &full[s]);
+          }
         }
+        if (end) break;
       }
     }
     return;
   }
 
-  /* ---- consumers ---- */
+  /* ---- consumers: follow the stage tags ---- */
   const int c0 = (2 * tid) % kNchBmf, c1 = (2 * tid + 1) % kNchBmf;
   const size_t nchan = (size_t)nchunk * kNchBmf;
-  uint32_t it = 0;
   bool waited = !early;
-  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const uint32_t group = item % ngroups, rest = item / ngroups;
-    const uint32_t split = rest % nsplit, beam = rest / nsplit;
-    uint64_t f0, f1;
-    split_range(ndf, split, nsplit, f0, f1);
-    T a[G][2];
+  T a[G][2];
 #pragma unroll
-    for (int g = 0; g < G; ++g) a[g][0] = a[g][1] = 0;
-
-    for (uint64_t f = f0; f < f1; ++f, ++it) {
-      const uint32_t s = it % NSTAGE, k = it / NSTAGE;
-      mbar_wait(&full[s], k & 1);
+  for (int g = 0; g < G; ++g) a[g][0] = a[g][1] = 0;
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t s = it % NSTAGE, k = it / NSTAGE;
+    mbar_wait(&full[s], k & 1);
+    const uint32_t t = tag[s];
+    if (t == kTagEnd) break;
+    if (!(t & 0x40000000u)) {
       const unsigned char *st = smem + s * S::kStageBytes + tid * 16;
       uint4 v[G];
 #pragma unroll
@@ -466,9 +491,16 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
         Acc::template add<BE>(a[g][0], v[g].x, v[g].y);
         Acc::template add<BE>(a[g][1], v[g].z, v[g].w);
       }
+    } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
     }
+    if (!(t & kTagLast)) continue;
 
     /* item done: G*7 channel totals of this (beam, split, group) */
+    const uint32_t item = t & 0x3FFFFFFFu;
+    const uint32_t group = item % ngroups, rest = item / ngroups;
+    const uint32_t split = rest % nsplit, beam = rest / nsplit;
     T *dst = partials + ((size_t)beam * nsplit + split) * nchan + (size_t)group * G * kNchBmf;
 #pragma unroll
     for (int g = 0; g < G; ++g)
@@ -486,6 +518,8 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
     }
     waited = true;
     consumer_bar(); /* red is reused by the next item */
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g][0] = a[g][1] = 0;
   }
 }
 
@@ -594,17 +628,17 @@ int b2p_tma_group(int nchunk)
 namespace {
 constexpr int kTmaStagesG4 = 7, kTmaStagesG2 = 14, kTmaStagesG1 = 28;
 
-template <typename Acc, bool BE, int G, int NSTAGE>
+template <typename Acc, bool BE, int G, int NSTAGE, int MINB = 1>
 cudaError_t launch_tma(const B2pLaunch &L, cudaStream_t st)
 {
   typedef TmaSmem<G, NSTAGE> S;
   const uint32_t ngroups = L.nchunk / G;
   const uint32_t nitems = (uint32_t)L.nbeam * L.nsplit * ngroups;
-  uint32_t grid = (uint32_t)L.sm_count;
+  uint32_t grid = (uint32_t)L.sm_count * MINB;
   if (grid > nitems) grid = nitems;
-  return launch_k(b2p_fused_tma_bmf<Acc, BE, G, NSTAGE>, dim3(grid), dim3(kTmaThreads), S::kBytes,
+  return launch_k(b2p_fused_tma_bmf<Acc, BE, G, NSTAGE, MINB>, dim3(grid), dim3(kTmaThreads), S::kBytes,
                   st, L.pdl != 0, L.beams, (uint32_t)L.nchunk, L.ndf, (uint32_t)L.nsplit, nitems,
-                  L.early, (typename Acc::type *)L.partials);
+                  L.early, L.ticket, (typename Acc::type *)L.partials);
 }
 
 template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, cudaStream_t st)
@@ -613,6 +647,9 @@ template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, 
   const bool bmf = b2p_is_bmf_geometry(L.nch, L.nsamp);
   const bool pdl = L.pdl != 0;
   if (L.kernel == B2P_KERNEL_TMA && bmf) {
+    if (L.variant == 1 && L.nchunk % 2 == 0) return launch_tma<Acc, BE, 2, kTmaStagesG2>(L, st);
+    if (L.variant == 2) return launch_tma<Acc, BE, 1, kTmaStagesG1>(L, st);
+    if (L.variant == 3) return launch_tma<Acc, BE, 1, 14, 2>(L, st); /* 2 CTAs/SM, 100 KB rings */
     switch (b2p_tma_group(L.nchunk)) {
       case 4: return launch_tma<Acc, BE, 4, kTmaStagesG4>(L, st);
       case 2: return launch_tma<Acc, BE, 2, kTmaStagesG2>(L, st);
@@ -648,9 +685,9 @@ template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, 
                   L.early, part);
 }
 
-template <typename Acc, bool BE, int G, int NSTAGE> cudaError_t configure_tma()
+template <typename Acc, bool BE, int G, int NSTAGE, int MINB = 1> cudaError_t configure_tma()
 {
-  return cudaFuncSetAttribute(b2p_fused_tma_bmf<Acc, BE, G, NSTAGE>,
+  return cudaFuncSetAttribute(b2p_fused_tma_bmf<Acc, BE, G, NSTAGE, MINB>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize,
                               TmaSmem<G, NSTAGE>::kBytes);
 }
@@ -659,6 +696,7 @@ template <typename Acc, bool BE> cudaError_t configure_all()
   cudaError_t e;
   if ((e = configure_tma<Acc, BE, 4, kTmaStagesG4>()) != cudaSuccess) return e;
   if ((e = configure_tma<Acc, BE, 2, kTmaStagesG2>()) != cudaSuccess) return e;
+  if ((e = configure_tma<Acc, BE, 1, 14, 2>()) != cudaSuccess) return e;
   return configure_tma<Acc, BE, 1, kTmaStagesG1>();
 }
 

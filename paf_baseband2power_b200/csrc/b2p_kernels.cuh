@@ -38,6 +38,7 @@ struct B2pLaunch {
   int pdl;         /* launch with programmatic stream serialization */
   int early;       /* input independent of the stream's previous kernel: start before it ends */
   uint64_t ndf;    /* frames per beam in this launch */
+  unsigned int *ticket; /* zeroed work-item counter of this launch (TMA kernel) */
   void *partials;  /* [nbeam][nsplit][nchan] uint64 (exact) or double (float mode) */
   void *acc;       /* [ctx nbeam][nchan]     uint64 (exact) or double (float mode) */
 };
