@@ -13,6 +13,7 @@
  *  -D dest ip [127.0.0.1]  -p first port [17100]  -P ports [6]  -n frames  -s seed  -m mode
  *  -r frames per second (0 = unpaced; line rate is 9259.26)  -S sec  -i idf  -e epoch  -b beam
  *  -f first chunk frequency MHz  -L drop every L-th packet (loss injection)  -A source prefix [127.0]
+ *  -C cache this many generated frames and repeat them (0 = all)  -T sender threads [1]
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -26,6 +27,7 @@
 #include <string.h>
 #include <sys/socket.h>
 #include <time.h>
+#include <omp.h>
 #include <unistd.h>
 
 #include "../../include/b2p_synth.h"
@@ -45,7 +47,9 @@ int main(int argc, char **argv)
   int epoch = 37, beam = 0, drop_every = 0, arg;
   uint64_t nframes = 64, seed = 1, sec0 = 27 * 1000, idf0 = 0;
   double rate = 2000.0, freq0 = 1173.0;
-  while ((arg = getopt(argc, argv, "D:p:P:n:s:m:r:S:i:e:b:f:L:A:h")) != -1) {
+  uint64_t cache = 0;
+  int nthreads = 1;
+  while ((arg = getopt(argc, argv, "D:p:P:n:s:m:r:S:i:e:b:f:L:A:C:T:h")) != -1) {
     switch (arg) {
       case 'D': snprintf(dest, sizeof(dest), "%s", optarg); break;
       case 'p': port_base = atoi(optarg); break;
@@ -61,6 +65,8 @@ int main(int argc, char **argv)
       case 'f': freq0 = atof(optarg); break;
       case 'L': drop_every = atoi(optarg); break;
       case 'A': snprintf(prefix, sizeof(prefix), "%s", optarg); break;
+      case 'C': cache = strtoull(optarg, NULL, 10); break;
+      case 'T': nthreads = atoi(optarg); break;
       default:
         fprintf(stdout, "bmf_replay -D dest -p port -P nports -n frames -s seed -m mode -r fps -S sec -i idf -e epoch -b beam -L drop_every\n");
         return EXIT_FAILURE;
@@ -91,50 +97,76 @@ int main(int argc, char **argv)
 
   const int nch = 7, nsamp = 128, nchan = nchunk * nch;
   const uint64_t wpp = (uint64_t)nch * nsamp; /* words per packet */
-  unsigned char *pkt = (unsigned char *)malloc(BMF_DF_SIZE);
-  uint64_t sent = 0, dropped = 0, counter = 0;
-  const double t0 = now_s();
-  for (uint64_t f = 0; f < nframes; ++f) {
-    uint64_t idf = idf0 + f, sec = sec0;
-    sec += (idf / BMF_NDF_PRD) * BMF_PRD_SEC; /* the frame counter wraps every period of 27 s */
-    idf %= BMF_NDF_PRD;
+  /* Payloads are generated up front (generation runs at ~0.2 GB/s, line rate is 3.2 GB/s):
+     frame f carries cached payload f % ncache, i.e. the stream repeats with that period
+     when more frames are sent than cached. */
+  const uint64_t ncache = (cache && cache < nframes) ? cache : nframes;
+  unsigned char *pool = (unsigned char *)malloc(ncache * (uint64_t)nchunk * BMF_DT_SIZE);
+  if (!pool) {
+    fprintf(stderr, "bmf_replay: can not allocate the payload cache\n");
+    return EXIT_FAILURE;
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t f = 0; f < (int64_t)ncache; ++f)
     for (int c = 0; c < nchunk; ++c) {
-      bmf_hdr_t h = {1, idf, sec, epoch, beam, freq0 + 7.0 * c};
-      bmf_hdr_encode(pkt, &h);
-      uint64_t *pay = (uint64_t *)(pkt + BMF_HDR_SIZE);
-      const uint64_t w0 = (f * (uint64_t)nchunk + (uint64_t)c) * wpp;
+      uint64_t *pay = (uint64_t *)(pool + ((uint64_t)f * nchunk + c) * BMF_DT_SIZE);
+      const uint64_t w0 = ((uint64_t)f * (uint64_t)nchunk + (uint64_t)c) * wpp;
       for (uint64_t k = 0; k < wpp; ++k) {
         int16_t v[4];
         b2p_synth_word(seed, w0 + k, c * nch + (int)(k % (uint64_t)nch), nchan, mode, v);
         pay[k] = b2p_synth_pack(v, 1);
       }
-      ++counter;
-      if (drop_every > 0 && counter % (uint64_t)drop_every == 0) {
-        ++dropped;
-        continue;
-      }
-      while (sendto(socks[c], pkt, BMF_DF_SIZE, 0, (struct sockaddr *)&dst[c], sizeof(dst[c])) < 0) {
-        if (errno == ENOBUFS || errno == EAGAIN || errno == EINTR) {
-          usleep(50);
+    }
+
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > nchunk) nthreads = nchunk;
+  uint64_t sent = 0, dropped = 0;
+  int failed = 0;
+  const double t0 = now_s();
+#pragma omp parallel num_threads(nthreads) reduction(+ : sent, dropped)
+  {
+    const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+    const int c_lo = nchunk * tid / nt, c_hi = nchunk * (tid + 1) / nt;
+    unsigned char *pkt = (unsigned char *)malloc(BMF_DF_SIZE);
+    for (uint64_t f = 0; f < nframes && !failed; ++f) {
+      uint64_t idf = idf0 + f, sec = sec0;
+      sec += (idf / BMF_NDF_PRD) * BMF_PRD_SEC; /* the frame counter wraps every period of 27 s */
+      idf %= BMF_NDF_PRD;
+      for (int c = c_lo; c < c_hi; ++c) {
+        bmf_hdr_t h = {1, idf, sec, epoch, beam, freq0 + 7.0 * c};
+        bmf_hdr_encode(pkt, &h);
+        memcpy(pkt + BMF_HDR_SIZE, pool + ((f % ncache) * (uint64_t)nchunk + (uint64_t)c) * BMF_DT_SIZE, BMF_DT_SIZE);
+        const uint64_t counter = f * (uint64_t)nchunk + (uint64_t)c + 1;
+        if (drop_every > 0 && counter % (uint64_t)drop_every == 0) {
+          ++dropped;
           continue;
         }
-        fprintf(stderr, "bmf_replay: sendto: %s\n", strerror(errno));
-        return EXIT_FAILURE;
+        while (sendto(socks[c], pkt, BMF_DF_SIZE, 0, (struct sockaddr *)&dst[c], sizeof(dst[c])) < 0) {
+          if (errno == ENOBUFS || errno == EAGAIN || errno == EINTR) {
+            usleep(20);
+            continue;
+          }
+          fprintf(stderr, "bmf_replay: sendto: %s\n", strerror(errno));
+          failed = 1;
+          break;
+        }
+        ++sent;
       }
-      ++sent;
-    }
-    if (rate > 0) { /* pace on absolute time so the average rate holds */
-      const double due = t0 + (double)(f + 1) / rate;
-      double dt = due - now_s();
-      if (dt > 0) {
-        struct timespec ts = {(time_t)dt, (long)((dt - (double)(time_t)dt) * 1e9)};
-        nanosleep(&ts, NULL);
+      if (rate > 0) { /* pace on absolute time so the average rate holds */
+        const double due = t0 + (double)(f + 1) / rate;
+        double dt = due - now_s();
+        if (dt > 0) {
+          struct timespec ts = {(time_t)dt, (long)((dt - (double)(time_t)dt) * 1e9)};
+          nanosleep(&ts, NULL);
+        }
       }
     }
+    free(pkt);
   }
+  if (failed) return EXIT_FAILURE;
   const double el = now_s() - t0;
-  printf("bmf_replay: %lu packets sent, %lu dropped on purpose, %lu frames in %.3f s (%.1f frames/s, %.3f GB/s)\n",
+  printf("bmf_replay: %lu packets sent, %lu dropped on purpose, %lu frames in %.3f s (%.1f frames/s, %.3f GB/s, %.2fx line rate)\n",
          (unsigned long)sent, (unsigned long)dropped, (unsigned long)nframes, el, (double)nframes / el,
-         (double)sent * BMF_DF_SIZE / el / 1e9);
+         (double)sent * BMF_DF_SIZE / el / 1e9, (double)nframes / el * BMF_TDF_SEC);
   return EXIT_SUCCESS;
 }

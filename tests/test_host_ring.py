@@ -152,3 +152,29 @@ def test_pipeline_diskdb_baseband2power_dbdisk(tmp_path, oracle_mod, b2p, kernel
     assert "TSAMP        %.4f" % tsamp in hdr and "NBIT         32" in hdr and "NCHAN        336" in hdr
     log = (tmp_path / "paf_baseband2power.log").read_text()
     assert "START PAF_PROCESS" in log and "5 spectra out" in log and "partial integration of 10 frames" in log
+
+
+@pytest.mark.gpu
+def test_memory_resident_stream_through_the_rings(tmp_path, oracle_mod, b2p):
+    """BASELINE.json configs[1] in miniature: paf_memdb publishes 11 blocks (3 distinct, generated in
+    place in the ring) -> paf_baseband2power -> paf_dbdisk; spectrum i is the oracle's for block i % 3."""
+    ndf, nbufs, nblk = 48, 3, 11
+    kin, kout = "%x" % _key(), "%x" % (_key() | 0x10000)
+    run(os.path.join(BIN, "paf_dada_db"), "-k", kin, "-b", str(ndf * FRAME), "-n", str(nbufs))
+    run(os.path.join(BIN, "paf_dada_db"), "-k", kout, "-b", "1344", "-n", "4")
+    try:
+        sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", kout, "-D", str(tmp_path), "-f", "s.dada", "-W"], stderr=subprocess.PIPE)
+        stage = subprocess.Popen([os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", str(tmp_path), "-d", "0"], stderr=subprocess.PIPE)
+        time.sleep(0.3)
+        run(os.path.join(BIN, "paf_memdb"), "-k", kin, "-n", str(nblk), "-s", "33", "-H", HDR)
+        assert stage.wait(timeout=120) == 0, stage.stderr.read().decode()
+        assert sink.wait(timeout=60) == 0
+    finally:
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", kin)
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", kout)
+    spectra = np.frombuffer((tmp_path / "s.dada").read_bytes()[4096:], dtype=np.float32).reshape(nblk, 336)
+    wpb = ndf * FRAME // 8
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(oracle_mod.synth_fill(ndf, seed=33, first_word=b * wpb, mode=1)))
+            for b in range(nbufs)]
+    for i in range(nblk):
+        assert np.array_equal(spectra[i].view(np.uint32), want[i % nbufs].view(np.uint32)), i
