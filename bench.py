@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 32)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ring", action="store_true", help="skip the executables-through-the-rings leg")
     ap.add_argument("--beamset", type=int, default=36, help="extra kernel-only point: full beam set on one GPU (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -413,6 +414,18 @@ def main():
         if not parity:
             raise SystemExit("bench.py: GPU spectrum differs from the CPU oracle — number withheld")
 
+    # ---- extra: the same stream through the real process surface (SysV rings + executables) ----
+    ring = None
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_ring and nbeam == 1:
+        try:
+            import importlib.util
+            spec_ = importlib.util.spec_from_file_location("run_ring_e2e", os.path.join(ROOT, "tools", "run_ring_e2e.py"))
+            mod = importlib.util.module_from_spec(spec_)
+            spec_.loader.exec_module(mod)
+            ring = mod.run(ndf=ndf, nbufs=4, nblocks=16, gpu=local, kernel=args.kernel)
+        except Exception as e:  # informational leg only
+            ring = {"error": repr(e)[:300]}
+
     # ---- extra: full beam set on one GPU, kernel-only (configs[2]) ----
     beamset = None
     if args.beamset and nbeam == 1 and args.beamset > 1:
@@ -472,7 +485,7 @@ def main():
             "samples_per_s": round(world * nbeam * ndf * 128 * g.nchan / (ms_step * 1e-3), 1),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "parity_vs_oracle": parity,
-            "beamset": beamset, "device": device_info(local)["name"],
+            "ring_e2e": ring, "beamset": beamset, "device": device_info(local)["name"],
         }))
     st.close()
     if world > 1:
