@@ -228,3 +228,65 @@ def test_caller_stream(b2p, oracle_mod, kernel):
             res = out.cpu().numpy()
             assert np.array_equal(res.view(np.uint32), want.view(np.uint32))
             st.close()
+
+
+def test_empty_inputs(b2p, oracle_mod):
+    st = b2p.Baseband2Power()
+    assert not st.finish().any()                      # finish with nothing accumulated -> zeros
+    dev = b2p.DeviceBuffer(48 * 7168)
+    st.accumulate_device([dev], 0)                    # zero frames is a no-op, not an error
+    assert not st.read_sums().any()
+    assert st.launch_count == 1                       # only the finish above launched anything
+    st.reset()
+    dev.free()
+    st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_block_bit_exact(b2p, oracle_mod, kernel):
+    """One full ring block (8192 frames, 2 818 572 288 B) against the oracle, device and host paths."""
+    ndf = 8192
+    block = oracle_mod.synth_fill(ndf, seed=4242, mode=1)
+    want = oracle_mod.accumulate_omp(block, nthreads=len(__import__("os").sched_getaffinity(0)))
+    st = b2p.Baseband2Power(kernel=kernel)
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.synth_fill(ndf, seed=4242, mode=1)            # device generator, same stream
+    st.accumulate_device([dev], ndf)
+    assert np.array_equal(st.read_sums()[0], want)
+    out = st.finish()[0]
+    assert np.array_equal(out.view(np.uint32), oracle_mod.finish(want).view(np.uint32))
+    st.accumulate_host([block], ndf)                  # pageable host memory, staged path
+    assert np.array_equal(st.finish()[0].view(np.uint32), out.view(np.uint32))
+    dev.free()
+    st.close()
+
+
+def test_full_scale_full_block_is_2_pow_52(b2p):
+    """Every component -32768 over a full integration: each channel is exactly 2^52 (the largest
+    value the spec can produce) — no overflow anywhere in the chain; mean scaling gives 2^32."""
+    ndf = 8192
+    dev = b2p.DeviceBuffer(ndf * 48 * 7168)
+    piece = np.tile(np.array([0x80, 0x00], dtype=np.uint8), 64 * 48 * 7168 // 2)   # 64 frames of 0x8000
+    for i in range(ndf // 64):
+        dev.upload(piece, offset=i * piece.nbytes)
+    for kernel in KERNELS:
+        st = b2p.Baseband2Power(kernel=kernel)
+        st.accumulate_device([dev], ndf)
+        assert np.all(st.read_sums() == np.uint64(1 << 52))
+        assert np.all(st.finish() == np.float32(2.0 ** 52))
+        st.close()
+        st = b2p.Baseband2Power(kernel=kernel, scale=2.0 ** -20)
+        st.accumulate_device([dev], ndf)
+        assert np.all(st.finish() == np.float32(2.0 ** 32))
+        st.close()
+    dev.free()
+
+
+def test_maximum_beam_count(b2p, oracle_mod):
+    nbeam, ndf = 64, 4
+    blocks = [oracle_mod.synth_fill(ndf, seed=b, mode=0) for b in range(nbeam)]
+    sums, _ = _run_device(b2p, np.concatenate(blocks), ndf, "ldg", nbeam=nbeam)
+    for b in (0, 1, 31, 63):
+        assert np.array_equal(sums[b], oracle_mod.accumulate(blocks[b])), b
+    with pytest.raises(b2p.B2pError):
+        b2p.Baseband2Power(nbeam=65)
