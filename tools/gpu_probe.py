@@ -14,6 +14,8 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--kernels", default="ldg,tma")
 ap.add_argument("--nsplits", default="0")
 ap.add_argument("--variants", default="0")
+ap.add_argument("--weaves", default="1")
+ap.add_argument("--mode", default="exact")
 args = ap.parse_args()
 
 print(json.dumps(device_info(0)))
@@ -26,9 +28,11 @@ ptrs = [buf.ptr + b * per for b in range(nb)]
 out = DeviceBuffer(nb * BMF.nchan * 4)
 for kernel in args.kernels.split(","):
   for variant in args.variants.split(","):
+   for weave in args.weaves.split(","):
     os.environ["B2P_VARIANT"] = variant
+    os.environ["B2P_WEAVE"] = weave
     for ns in [int(x) for x in args.nsplits.split(",")]:
-        st = Baseband2Power(kernel=kernel, nbeam=nb, nsplit=ns)
+        st = Baseband2Power(kernel=kernel, nbeam=nb, nsplit=ns, mode=args.mode)
         for _ in range(3):
             st.accumulate_device(ptrs, ndf)
             st.finish_device(out)
@@ -46,7 +50,7 @@ for kernel in args.kernels.split(","):
         times.sort()
         best, med = times[0], times[len(times) // 2]
         gb = nb * per / 1e9
-        print(json.dumps({"kernel": kernel, "variant": variant, "nsplit": st.nsplit, "nbeam": nb, "ndf": ndf,
+        print(json.dumps({"kernel": kernel, "variant": variant, "weave": weave, "mode": args.mode, "nsplit": st.nsplit, "nbeam": nb, "ndf": ndf,
                           "match": match, "best_ms": round(best, 4), "median_ms": round(med, 4),
                           "best_GBps": round(gb / best * 1e3, 1), "median_GBps": round(gb / med * 1e3, 1)}),
               flush=True)
