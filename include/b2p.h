@@ -93,6 +93,13 @@ const char *b2p_last_error(const b2p_ctx *ctx);
  * block[idf][chunk][t][ch][pol][re,im] (capture.c:540-542).  Adds into the
  * context's accumulators; asynchronous on `stream`.  An integration is any
  * sequence of accumulate calls closed by b2p_finish*.
+ *
+ * Stream rule: on a caller's stream the kernels obey ordinary stream order (the
+ * input may be produced by the caller's previous kernel on that stream).  With
+ * stream == NULL they run on the context's own stream, where a fused kernel is
+ * allowed to start reading its input while the context's previous kernel is
+ * still finishing (programmatic dependent launch) — so the input must be
+ * complete when the call is made (synchronise the producer first).
  */
 int b2p_accumulate_device(b2p_ctx *ctx, const void *const *dptrs, uint64_t ndf, void *stream);
 
