@@ -44,7 +44,7 @@ extern "C" {
 
 /* fused-kernel variants */
 #define B2P_KERNEL_AUTO 0
-#define B2P_KERNEL_LDG  1 /* 128-bit coalesced streaming loads, register pipeline */
+#define B2P_KERNEL_LDG  1 /* 256-bit coalesced evict-first streaming loads, register pipeline */
 #define B2P_KERNEL_TMA  2 /* cp.async.bulk + mbarrier multi-stage shared-memory ring */
 
 #define B2P_MAX_BEAMS 64
