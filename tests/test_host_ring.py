@@ -178,3 +178,37 @@ def test_memory_resident_stream_through_the_rings(tmp_path, oracle_mod, b2p):
             for b in range(nbufs)]
     for i in range(nblk):
         assert np.array_equal(spectra[i].view(np.uint32), want[i % nbufs].view(np.uint32)), i
+
+
+@pytest.mark.gpu
+def test_stage_options_average_and_multi_block_integration(tmp_path, oracle_mod, b2p):
+    """-s 1 (time average: scale 1/(frames*128)) and -n (an integration spanning two ring blocks)."""
+    ndf_block, nblk = 32, 5
+    kin, kout = "%x" % _key(), "%x" % (_key() | 0x10000)
+    src = tmp_path / "in.dada"
+    run(os.path.join(BIN, "b2p_gen"), "-o", str(src), "-n", str(ndf_block * nblk), "-s", "8", "-H", HDR)
+    run(os.path.join(BIN, "paf_dada_db"), "-k", kin, "-b", str(ndf_block * FRAME), "-n", "3")
+    run(os.path.join(BIN, "paf_dada_db"), "-k", kout, "-b", "1344", "-n", "4")
+    try:
+        sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", kout, "-D", str(tmp_path), "-f", "s.dada", "-W"], stderr=subprocess.PIPE)
+        stage = subprocess.Popen([os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", str(tmp_path), "-d", "0",
+                                  "-s", "1", "-n", str(2 * ndf_block), "-p", "0"], stderr=subprocess.PIPE)
+        time.sleep(0.3)
+        run(os.path.join(BIN, "paf_diskdb"), "-a", kin, "-b", str(tmp_path), "-c", "in.dada", "-d", HDR, "-e", "1")
+        assert stage.wait(timeout=120) == 0, stage.stderr.read().decode()
+        assert sink.wait(timeout=60) == 0
+    finally:
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", kin)
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", kout)
+    out = (tmp_path / "s.dada").read_bytes()
+    spectra = np.frombuffer(out[4096:], dtype=np.float32).reshape(-1, 336)
+    assert spectra.shape[0] == 2                                   # 5 blocks -> 2 integrations of 2 blocks, 1 block left over
+    payload = np.fromfile(src, dtype=np.uint8)[4096:]
+    per = 2 * ndf_block * FRAME
+    scale = 1.0 / (2 * ndf_block * 128)                            # 2^-13
+    for i in range(2):
+        want = oracle_mod.finish(oracle_mod.accumulate_omp(payload[i * per:(i + 1) * per]), scale)
+        assert np.array_equal(spectra[i].view(np.uint32), want.view(np.uint32)), i
+    hdr = out[:4096].rstrip(b"\0").decode()
+    assert "TSAMP        %.4f" % (2 * ndf_block * 128 * 27.0 / 32.0) in hdr
+    assert "partial integration of 32 frames" in (tmp_path / "paf_baseband2power.log").read_text()
