@@ -12,109 +12,87 @@
 #define _GNU_SOURCE
 #endif
 
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
 #include <unistd.h>
 
 #include "../../include/b2p.h"
 #include "../../include/baseband2power.h"
-#include "dada/multilog.h"
+#include "cli_util.h"
 
 multilog_t *runtime_log;
 
-static void usage(void)
+static const char *const kUsage[] = {
+    "paf_baseband2power - To detect baseband data with original channels and integrate the detected data in time",
+    "",
+    "Usage: paf_baseband2power [options]",
+    " -a  Hexadecimal shared memory key for incoming ring buffer",
+    " -b  Hexadecimal shared memory key for outcoming ring buffer",
+    " -c  The name of the directory in which we will record the data",
+    " -d  The index of GPU",
+    " -h  show help",
+    "extensions:",
+    " -s  0 integral over the integration (default), 1 average in time",
+    " -n  data frames per integration (default: frames of one input block)",
+    " -k  kernel: auto | ldg | tma",
+    " -e  1 big-endian samples (default), 0 little-endian",
+    " -p  1 page-lock the input ring (default), 0 leave it pageable",
+    NULL};
+
+static int kernel_by_name(const char *name)
 {
-  fprintf(stdout,
-          "paf_baseband2power - To detect baseband data with original channels and integrate the "
-          "detected data in time\n"
-          "\n"
-          "Usage: paf_baseband2power [options]\n"
-          " -a  Hexadecimal shared memory key for incoming ring buffer\n"
-          " -b  Hexadecimal shared memory key for outcoming ring buffer\n"
-          " -c  The name of the directory in which we will record the data\n"
-          " -d  The index of GPU\n"
-          " -h  show help\n"
-          "extensions:\n"
-          " -s  0 integral over the integration (default), 1 average in time\n"
-          " -n  data frames per integration (default: frames of one input block)\n"
-          " -k  kernel: auto | ldg | tma\n"
-          " -e  1 big-endian samples (default), 0 little-endian\n"
-          " -p  1 page-lock the input ring (default), 0 leave it pageable\n");
+  if (!strcmp(name, "tma")) return B2P_KERNEL_TMA;
+  if (!strcmp(name, "ldg")) return B2P_KERNEL_LDG;
+  return B2P_KERNEL_AUTO;
+}
+
+/* returns 0 to go on, 1 to leave with EXIT_FAILURE (help or a bad option) */
+static int parse_args(int argc, char *argv[], conf_t *conf)
+{
+  for (int opt; (opt = getopt(argc, argv, "a:b:c:d:hs:n:k:e:p:")) != -1;) {
+    if (opt == 'a' || opt == 'b') {
+      if (cli_hex_key(optarg, opt == 'a' ? &conf->key_in : &conf->key_out, __FILE__, __LINE__)) return 1;
+    } else if (opt == 'c') {
+      cli_copy(conf->dir, MSTR_LEN, optarg);
+    } else if (opt == 'd') {
+      conf->device_id = atoi(optarg);
+    } else if (opt == 's') {
+      conf->average = atoi(optarg) != 0;
+    } else if (opt == 'n') {
+      conf->ndf_integration = strtoull(optarg, NULL, 10);
+    } else if (opt == 'k') {
+      conf->kernel = kernel_by_name(optarg);
+    } else if (opt == 'e') {
+      conf->big_endian = atoi(optarg) != 0;
+    } else if (opt == 'p') {
+      conf->pin_ring = atoi(optarg) != 0;
+    } else { /* -h and anything unknown */
+      cli_print_lines(stdout, kUsage);
+      return 1;
+    }
+  }
+  return 0;
 }
 
 int main(int argc, char *argv[])
 {
-  int arg;
   conf_t conf;
   default_baseband2power(&conf);
+  if (parse_args(argc, argv, &conf)) return EXIT_FAILURE;
 
-  while ((arg = getopt(argc, argv, "a:b:c:d:hs:n:k:e:p:")) != -1) {
-    switch (arg) {
-      case 'h':
-        usage();
-        return EXIT_FAILURE;
-      case 'a':
-        if (sscanf(optarg, "%x", (unsigned *)&conf.key_in) != 1) {
-          fprintf(stderr, "Could not parse key from %s, which happens at \"%s\", line [%d].\n", optarg, __FILE__, __LINE__);
-          return EXIT_FAILURE;
-        }
-        break;
-      case 'b':
-        if (sscanf(optarg, "%x", (unsigned *)&conf.key_out) != 1) {
-          fprintf(stderr, "Could not parse key from %s, which happens at \"%s\", line [%d].\n", optarg, __FILE__, __LINE__);
-          return EXIT_FAILURE;
-        }
-        break;
-      case 'c':
-        snprintf(conf.dir, MSTR_LEN, "%s", optarg);
-        break;
-      case 'd':
-        conf.device_id = atoi(optarg);
-        break;
-      case 's':
-        conf.average = atoi(optarg) ? 1 : 0;
-        break;
-      case 'n':
-        conf.ndf_integration = strtoull(optarg, NULL, 10);
-        break;
-      case 'k':
-        conf.kernel = !strcmp(optarg, "tma") ? B2P_KERNEL_TMA : (!strcmp(optarg, "ldg") ? B2P_KERNEL_LDG : B2P_KERNEL_AUTO);
-        break;
-      case 'e':
-        conf.big_endian = atoi(optarg) ? 1 : 0;
-        break;
-      case 'p':
-        conf.pin_ring = atoi(optarg) ? 1 : 0;
-        break;
-      default:
-        usage();
-        return EXIT_FAILURE;
-    }
-  }
-
-  /* Setup log interface */
-  char log_fname[MSTR_LEN + 64];
-  snprintf(log_fname, sizeof(log_fname), "%s/paf_baseband2power.log", conf.dir);
-  FILE *fp_log = fopen(log_fname, "ab+");
-  if (fp_log == NULL) {
-    fprintf(stderr, "Can not open log file %s\n", log_fname);
-    return EXIT_FAILURE;
-  }
-  runtime_log = multilog_open("paf_baseband2power", 1);
-  multilog_add(runtime_log, fp_log);
+  FILE *fp_log = NULL;
+  runtime_log = cli_open_log(conf.dir, "paf_baseband2power", &fp_log);
+  if (!runtime_log) return EXIT_FAILURE;
   multilog(runtime_log, LOG_INFO, "START PAF_PROCESS\n");
   conf.log = runtime_log;
 
-  /* one GPU exposed to the container: its index is 0 whatever -d says */
+  /* a container that exposes a single GPU numbers it 0 whatever -d says */
   if (b2p_device_count() == 1) conf.device_id = 0;
 
-  int rc = init_baseband2power(&conf);
-  if (rc == EXIT_SUCCESS) rc = do_baseband2power(&conf);
+  int status = init_baseband2power(&conf);
+  if (status == EXIT_SUCCESS) status = do_baseband2power(&conf);
   destroy_baseband2power(&conf);
 
   multilog(runtime_log, LOG_INFO, "FINISH PAF_PROCESS\n");
   multilog_close(runtime_log);
   fclose(fp_log);
-  return rc;
+  return status;
 }

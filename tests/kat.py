@@ -87,3 +87,14 @@ def all_kats(ndf=4, nchunk=48, nch=7, nsamp=128, big_endian=True):
     for i, (a, b, c, d) in enumerate(corners):
         out[f"single_{i}"] = kat_single_word(a, b, c, d, **kw)
     return out
+
+
+def hdr_kv(text):
+    """DADA header text -> {key: value} (comments and padding dropped)."""
+    out = {}
+    for line in text.splitlines():
+        line = line.split("#")[0].strip()
+        if line:
+            p = line.split(None, 1)
+            out[p[0]] = p[1].strip() if len(p) > 1 else ""
+    return out

@@ -11,6 +11,8 @@ import time
 import numpy as np
 import pytest
 
+from tests.kat import hdr_kv
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "paf_baseband2power_b200")
 BIN = os.path.join(PKG, "bin")
@@ -113,8 +115,9 @@ def test_capture_assembles_the_generator_block(tmp_path, oracle_mod):
     assert recv == equal and missing == zero and recv + missing == expected
     assert equal >= 0.9 * npk_cap                       # loopback at 800 frames/s should lose ~nothing
     hdr = bytes(data[:4096]).rstrip(b"\0").decode()
-    assert "UTC_START    2018-07-02-10:30:26" in hdr and "FREQ         1340.5" in hdr   # 27000 s + 249990*108us
-    assert "PICOSECONDS  998920000000" in hdr
+    kv = hdr_kv(hdr)
+    assert kv["UTC_START"] == "2018-07-02-10:30:26" and kv["FREQ"] == "1340.5"   # 27000 s + 249990*108us
+    assert kv["PICOSECONDS"] == "998920000000" and kv["INSTRUMENT"] == "PAF-BMF"
 
 
 def test_capture_zero_fills_injected_loss(tmp_path, oracle_mod):

@@ -9,6 +9,8 @@ import time
 import numpy as np
 import pytest
 
+from tests.kat import hdr_kv
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "paf_baseband2power_b200")
 BIN = os.path.join(PKG, "bin")
@@ -75,8 +77,8 @@ def test_diskdb_ring_dbdisk_roundtrip(tmp_path, ndf_file, ndf_block, nbufs):
     assert len(b) == 4096 + ndf_file * FRAME
     assert a[4096:] == b[4096:]
     hdr = b[:4096].rstrip(b"\0").decode()
-    assert "FILE_SIZE    %d" % (ndf_file * FRAME) in hdr
-    assert "INSTRUMENT   PAF-BMF" in hdr       # ring header came from the template (diskdb.cu:79-85)
+    assert hdr_kv(hdr)["FILE_SIZE"] == str(ndf_file * FRAME)
+    assert hdr_kv(hdr)["INSTRUMENT"] == "PAF-BMF"   # ring header came from the template (diskdb.cu:79-85)
 
 
 def test_second_writer_is_refused(tmp_path):
@@ -112,7 +114,7 @@ def test_b2p_gen_matches_oracle_generator(tmp_path, oracle_mod):
     data = np.fromfile(tmp_path / "g.dada", dtype=np.uint8)
     assert np.array_equal(data[4096:], oracle_mod.synth_fill(3, seed=77, mode=0))
     hdr = bytes(data[:4096]).rstrip(b"\0").decode()
-    assert "UTC_START    2026-10-18-00:00:00" in hdr and "NBIT         16" in hdr
+    assert hdr_kv(hdr)["UTC_START"] == "2026-10-18-00:00:00" and hdr_kv(hdr)["NBIT"] == "16"
 
 
 @pytest.mark.gpu
@@ -149,7 +151,8 @@ def test_pipeline_diskdb_baseband2power_dbdisk(tmp_path, oracle_mod, b2p, kernel
         assert np.array_equal(spectra[i].view(np.uint32), want.view(np.uint32)), i
     hdr = out[:4096].rstrip(b"\0").decode()
     tsamp = ndf_block * 128 * 27.0 / 32.0
-    assert "TSAMP        %.4f" % tsamp in hdr and "NBIT         32" in hdr and "NCHAN        336" in hdr
+    kv = hdr_kv(hdr)
+    assert kv["TSAMP"] == "%.4f" % tsamp and kv["NBIT"] == "32" and kv["NCHAN"] == "336"
     log = (tmp_path / "paf_baseband2power.log").read_text()
     assert "START PAF_PROCESS" in log and "5 spectra out" in log and "partial integration of 10 frames" in log
 
@@ -210,5 +213,5 @@ def test_stage_options_average_and_multi_block_integration(tmp_path, oracle_mod,
         want = oracle_mod.finish(oracle_mod.accumulate_omp(payload[i * per:(i + 1) * per]), scale)
         assert np.array_equal(spectra[i].view(np.uint32), want.view(np.uint32)), i
     hdr = out[:4096].rstrip(b"\0").decode()
-    assert "TSAMP        %.4f" % (2 * ndf_block * 128 * 27.0 / 32.0) in hdr
+    assert hdr_kv(hdr)["TSAMP"] == "%.4f" % (2 * ndf_block * 128 * 27.0 / 32.0)
     assert "partial integration of 32 frames" in (tmp_path / "paf_baseband2power.log").read_text()
