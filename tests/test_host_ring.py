@@ -215,3 +215,22 @@ def test_stage_options_average_and_multi_block_integration(tmp_path, oracle_mod,
     hdr = out[:4096].rstrip(b"\0").decode()
     assert hdr_kv(hdr)["TSAMP"] == "%.4f" % (2 * ndf_block * 128 * 27.0 / 32.0)
     assert "partial integration of 32 frames" in (tmp_path / "paf_baseband2power.log").read_text()
+
+
+def test_ring_is_reusable_for_a_second_observation(tmp_path):
+    """Rings persist across runs in the reference's design (dada_db -p, paf-baseband2power.py:114):
+    after end-of-data has been consumed, a new writer/reader pair starts a fresh observation."""
+    key = "%x" % _key()
+    run(os.path.join(BIN, "paf_dada_db"), "-k", key, "-b", str(2 * FRAME), "-n", "3")
+    try:
+        for obs, (nfr, seed) in enumerate([(5, 1), (4, 2)]):
+            src, name = tmp_path / f"in{obs}.dada", f"out{obs}.dada"
+            run(os.path.join(BIN, "b2p_gen"), "-o", str(src), "-n", str(nfr), "-s", str(seed), "-H", HDR)
+            reader = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", key, "-D", str(tmp_path), "-f", name, "-W"],
+                                      stderr=subprocess.PIPE)
+            time.sleep(0.2)
+            run(os.path.join(BIN, "paf_diskdb"), "-a", key, "-b", str(tmp_path), "-c", src.name, "-d", HDR, "-e", "1")
+            assert reader.wait(timeout=60) == 0
+            assert src.read_bytes()[4096:] == (tmp_path / name).read_bytes()[4096:]
+    finally:
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", key)
