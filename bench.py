@@ -371,7 +371,7 @@ def main():
         e2e_ms = max_over_ranks(dt * 1e3) / ke
         e2e = {"value": round(world * nbeam * blk / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": nbeam * blk, "d2h_bytes_per_step": nbeam * g.out_bytes,
-               "ms_per_step": round(e2e_ms, 3), "steps": ke,
+               "ms_per_step": round(e2e_ms, 3), "steps": ke, "host_threads_per_gpu": 1,
                "realtime_factor": round(world * nbeam * g.t_integration_s * ndf / 8192 / (e2e_ms * 1e-3), 2),
                "h2d_link_GBps_per_gpu": round(h2d_link, 2),
                "frac_of_h2d_link": round(nbeam * blk / (e2e_ms * 1e-3) / 1e9 / h2d_link, 4),
