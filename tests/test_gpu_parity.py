@@ -290,3 +290,48 @@ def test_maximum_beam_count(b2p, oracle_mod):
         assert np.array_equal(sums[b], oracle_mod.accumulate(blocks[b])), b
     with pytest.raises(b2p.B2pError):
         b2p.Baseband2Power(nbeam=65)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_mixed_host_and_device_calls_multibeam(b2p, oracle_mod, kernel):
+    """One integration fed by host blocks, device blocks and mapped host blocks for 3 beams."""
+    nbeam, ndf = 3, 40
+    g = oracle_mod.Geometry()
+    hb = [oracle_mod.synth_fill(ndf, seed=600 + b, mode=1) for b in range(nbeam)]
+    db = [oracle_mod.synth_fill(ndf, seed=700 + b, mode=0) for b in range(nbeam)]
+    st = b2p.Baseband2Power(kernel=kernel, nbeam=nbeam, stage_ndf=16)
+    dev = b2p.DeviceBuffer(nbeam * db[0].nbytes)
+    dev.upload(np.concatenate(db))
+    pins = [b2p.PinnedBuffer(hb[b].nbytes) for b in range(nbeam)]
+    for b in range(nbeam):
+        pins[b].array[:] = hb[b]
+    st.accumulate_host(hb, ndf)
+    st.accumulate_device([dev.ptr + b * db[0].nbytes for b in range(nbeam)], ndf)
+    st.accumulate_host_mapped(pins, ndf)
+    sums = st.read_sums()
+    out = st.finish()
+    for b in range(nbeam):
+        want = oracle_mod.accumulate(hb[b]) * np.uint64(2) + oracle_mod.accumulate(db[b])
+        assert np.array_equal(sums[b], want), b
+        assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(want).view(np.uint32))
+    for p in pins:
+        p.free()
+    dev.free()
+    st.close()
+
+
+def test_float_mode_spans_calls(b2p, oracle_mod):
+    block = oracle_mod.synth_fill(96, seed=12, mode=1)
+    exact = oracle_mod.accumulate_omp(block).astype(np.float64)
+    g = oracle_mod.Geometry()
+    st = b2p.Baseband2Power(mode="float")
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    for f0, n in [(0, 32), (32, 1), (33, 63)]:
+        st.accumulate_device([dev.ptr + f0 * g.frame_bytes], n)
+    out = st.finish()[0].astype(np.float64)
+    assert (np.abs(out - exact) / exact).max() <= 1e-6
+    with pytest.raises(b2p.B2pError):
+        st.read_sums()                      # exact-mode accessor
+    dev.free()
+    st.close()
