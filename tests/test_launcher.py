@@ -67,7 +67,8 @@ def test_two_beam_pipeline_through_the_launcher(tmp_path, oracle_mod, b2p):
         names.append(f"beam{b}.dada")
         subprocess.run([os.path.join(BIN, "b2p_gen"), "-o", str(tmp_path / names[-1]), "-n", str(ndf_block * nblk),
                         "-s", str(40 + b), "-H", hdr], check=True, capture_output=True)
-    rc = launcher.main(["-a", CONF, "-b", str(tmp_path), "-c", "0", "-d", "", "-e", "0", "-f", *names,
+    gpus = ["0", "1"] if b2p.device_count() >= 2 else ["0"]     # beams round-robin over the GPUs present
+    rc = launcher.main(["-a", CONF, "-b", str(tmp_path), "-c", *gpus, "-d", "", "-e", "0", "-f", *names,
                         "--ndf", str(ndf_block), "--nblk", "3", "--timeout", "120"])
     assert rc == 0
     assert (tmp_path / "diskdb.key.beam00").read_text().startswith("DADA INFO:\nkey ")
