@@ -34,8 +34,9 @@
  *
  * What pins it in place of reference vectors: the hand-computable known-answer
  * tests of SURVEY.md §8c (tests/test_oracle_kat.py), an independent numpy
- * restatement (oracle/b2p_oracle_np.py), and committed fixtures generated from
- * both (tests/golden/).
+ * restatement (oracle/b2p_oracle_np.py), committed fixtures generated from
+ * both (tests/golden/), and — for the byte order alone — vectors produced by the
+ * reference's own BSWAP_64 macro (tests/golden/bswap64_vectors.json).
  */
 #include <stdint.h>
 #include <stdlib.h>

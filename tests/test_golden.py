@@ -108,3 +108,41 @@ def test_gpu_against_golden(b2p):
     assert [str(int(x)) for x in st.read_sums()[0]] == t["sums"]
     st.close()
     dev.free()
+
+
+def _bswap_vectors():
+    v = _load("bswap64_vectors.json")["vectors"]
+    words = np.array([int(x["word"], 16) for x in v], dtype=np.uint64)
+    swapped = np.array([int(x["bswap"], 16) for x in v], dtype=np.uint64)
+    return words, swapped
+
+
+def test_byte_order_agrees_with_the_reference_bswap64(oracle_mod):
+    """cudautil.cuh:118-125: the reference's GPU code was to byte-swap each 64-bit payload word.
+    Reading the four native int16 lanes of BSWAP_64(word) gives, in reverse order, exactly the
+    big-endian components this repo decodes from the word's memory bytes."""
+    words, swapped = _bswap_vectors()
+    ours = words.view(np.uint8).reshape(-1, 8).copy().view(">i2").astype(np.int64)       # [n][4] in memory order
+    ref = swapped.view("<i2").reshape(-1, 4).astype(np.int64)                            # native lanes of the swapped word
+    assert np.array_equal(ours, ref[:, ::-1])
+    # and through the oracle: one channel, sum of all squares
+    g = oracle_mod.Geometry(nchunk=1, nch_per_chunk=1, nsamp_df=2)
+    got = oracle_mod.accumulate(words.view(np.uint8), g=g)
+    assert int(got[0]) == int((ref * ref).sum())
+    # little-endian reading is what you get WITHOUT the swap
+    le = oracle_mod.accumulate(words.view(np.uint8), g=oracle_mod.Geometry(nchunk=1, nch_per_chunk=1, nsamp_df=2, big_endian=False))
+    native = words.view("<i2").astype(np.int64)
+    assert int(le[0]) == int((native * native).sum())
+
+
+@pytest.mark.gpu
+def test_gpu_byte_order_agrees_with_the_reference_bswap64(b2p):
+    words, swapped = _bswap_vectors()
+    ref = swapped.view("<i2").astype(np.int64)
+    st = b2p.Baseband2Power(nchunk=1, nch_per_chunk=1, nsamp_df=2)
+    dev = b2p.DeviceBuffer(words.nbytes)
+    dev.upload(words.view(np.uint8))
+    st.accumulate_device([dev], words.size // 2)
+    assert int(st.read_sums()[0, 0]) == int((ref * ref).sum())
+    st.close()
+    dev.free()

@@ -7,6 +7,8 @@
   bmf_hdr_vectors.json      BMF packet-header decode vectors produced by the REFERENCE's own
                             hdr.c (the one source file that compiles standalone), built by
                             oracle/Makefile into oracle/_ref/libpafhdr_ref.so.
+  bswap64_vectors.json      payload words through the REFERENCE's BSWAP_64 macro (cudautil.cuh:118-125),
+                            the only byte-order statement the reference makes for the GPU side.
   oracle_vectors.json       spectra of seeded synthetic blocks: sha256 of the block, exact
                             uint64 sums, float32 bit patterns.  Computed with the numpy
                             restatement and cross-checked against the C oracle here.  The
@@ -79,6 +81,19 @@ def bmf_hdr_vectors(n=64):
             "vectors": vec}
 
 
+def bswap64_vectors(n=96):
+    """The reference's only statement about sample byte order is the unused BSWAP_64 macro in
+    the GPU utility header (cudautil.cuh:118-125): record what it does to payload words."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libbswap_ref.so"))
+    lib.ref_bswap_64.restype = ctypes.c_uint64
+    lib.ref_bswap_64.argtypes = [ctypes.c_uint64]
+    rng = np.random.default_rng(118125)
+    words = [int(x) for x in rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)]
+    words[:4] = [0, 2 ** 64 - 1, 0x0001000200030004, 0x8000800080008000]
+    return {"source": "reference cudautil.cuh:118-125 (BSWAP_64) via oracle/ref_bswap_wrap.cpp -> oracle/_ref/libbswap_ref.so",
+            "vectors": [{"word": "%016x" % w, "bswap": "%016x" % lib.ref_bswap_64(w)} for w in words]}
+
+
 def oracle_vectors():
     cases = [(1, 0, 1, 0), (2, 1, 1, 0), (3, 0, 3, 12345), (4, 1, 5, 352321536), (20240517, 1, 8, 0),
              (7, 0, 2, 2 ** 40)]
@@ -124,6 +139,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     oracle.build()
     for name, fn in [("reference_artifacts", reference_artifacts), ("bmf_hdr_vectors", bmf_hdr_vectors),
+                     ("bswap64_vectors", bswap64_vectors),
                      ("oracle_vectors", oracle_vectors), ("tiny_block", tiny_block)]:
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(fn(), f, indent=1)
