@@ -190,3 +190,43 @@ def test_live_pipeline_replay_capture_baseband2power(tmp_path, oracle_mod, b2p):
             assert missing > 0 and np.all(spectra[i] <= want)   # lost packets only remove power
     assert exact == nblk or missing > 0
     assert exact >= 1
+
+
+def test_capture_can_keep_the_frame_headers(tmp_path, oracle_mod):
+    """-d 1 (debug mode of the reference, capture.c:216,222): the ring holds whole 7232-byte frames."""
+    ndf_block, ncap = 8, 16
+    DF = 7232
+    key = "%x" % (random.randint(0x2000, 0xDFFF) & 0xFFF0)
+    port = random.randint(20000, 40000)
+    run = lambda *c: subprocess.run(list(c), check=True, capture_output=True, text=True, timeout=120)
+    run(os.path.join(BIN, "paf_dada_db"), "-k", key, "-b", str(ndf_block * 48 * DF), "-n", "4")
+    sink = cap = None
+    try:
+        sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", key, "-D", str(tmp_path), "-f", "cap.dada", "-W"], stderr=subprocess.PIPE)
+        cap = subprocess.Popen([os.path.join(BIN, "paf_capture"), "-a", key, "-b", "1", "-c", str(ndf_block), "-d", "1", "-f", HDR, "-g", "none",
+                                "-i", "1340.5", "-j", repr(ncap * 1.08e-4), "-k", str(tmp_path), "-I", "127.0.0.1", "-p", str(port), "-t", "3"],
+                               stderr=subprocess.PIPE)
+        time.sleep(0.5)
+        run(os.path.join(BIN, "bmf_replay"), "-D", "127.0.0.1", "-p", str(port), "-n", str(ncap + 2), "-s", "4", "-r", "500", "-i", "100", "-b", "5")
+        assert cap.wait(timeout=60) == 0, cap.stderr.read().decode()
+        assert sink.wait(timeout=60) == 0
+    finally:
+        for p_ in (cap, sink):
+            if p_ is not None and p_.poll() is None:
+                p_.kill()
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", key)
+    frames = np.fromfile(tmp_path / "cap.dada", dtype=np.uint8)[4096:].reshape(-1, 48, DF)
+    want = oracle_mod.synth_fill(ncap, seed=4, mode=1).reshape(ncap, 48, PKT)
+    seen = 0
+    for f in range(ncap):
+        for c in range(48):
+            fr = frames[f, c]
+            if not fr.any():
+                continue
+            seen += 1
+            w0 = int.from_bytes(bytes(fr[0:8]), "big")
+            w2 = int.from_bytes(bytes(fr[16:24]), "big")
+            assert (w0 & 0xFFFFFFFF) == 100 + f and (w0 >> 63) == 1          # idf, valid (hdr.c:15-18)
+            assert (w2 & 0xFFFF) == 5 and ((w2 >> 16) & 0xFFFF) == 1173 + 7 * c   # beam, chunk frequency (hdr.c:23-25)
+            assert np.array_equal(fr[64:], want[f, c])
+    assert seen >= 0.9 * ncap * 48
