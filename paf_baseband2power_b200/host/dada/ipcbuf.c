@@ -6,6 +6,7 @@
 #include <string.h>
 #include <sys/ipc.h>
 #include <sys/shm.h>
+#include <time.h>
 
 static int lock(ipcsync_t *s)
 {
@@ -17,6 +18,23 @@ static int lock(ipcsync_t *s)
   return r;
 }
 static void unlock(ipcsync_t *s) { pthread_mutex_unlock(&s->mtx); }
+
+/* Wait for a state change, but wake at least every 200 ms so that a waiter notices when the
+   ring has been destroyed under it (magic cleared) instead of sleeping forever.
+   Returns 0 while the ring is alive. */
+static int wait_change(ipcsync_t *s)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  ts.tv_nsec += 200000000L;
+  if (ts.tv_nsec >= 1000000000L) {
+    ts.tv_sec += 1;
+    ts.tv_nsec -= 1000000000L;
+  }
+  int r = pthread_cond_timedwait(&s->cv, &s->mtx, &ts);
+  if (r == EOWNERDEAD) pthread_mutex_consistent(&s->mtx);
+  return s->magic == IPCBUF_MAGIC ? 0 : -1;
+}
 
 static int attach_buffers(ipcbuf_t *id)
 {
@@ -120,6 +138,10 @@ int ipcbuf_destroy(ipcbuf_t *id)
 {
   if (!id || !id->sync) return -1;
   ipcsync_t *s = id->sync;
+  lock(s);
+  s->magic = 0; /* tell every attached waiter that the ring is gone */
+  pthread_cond_broadcast(&s->cv);
+  unlock(s);
   for (uint64_t i = 0; i < s->nbufs; ++i) shmctl(s->shmid[i], IPC_RMID, NULL);
   int sid = id->syncid;
   ipcbuf_disconnect(id);
@@ -257,7 +279,11 @@ char *ipcbuf_get_next_write(ipcbuf_t *id)
   if (!id || !id->sync || !id->is_writer) return NULL;
   ipcsync_t *s = id->sync;
   lock(s);
-  while (s->w_count - s->r_count >= s->nbufs) pthread_cond_wait(&s->cv, &s->mtx);
+  while (s->w_count - s->r_count >= s->nbufs)
+    if (wait_change(s) < 0) {
+      unlock(s);
+      return NULL;
+    }
   char *p = id->buffer[s->w_count % s->nbufs];
   unlock(s);
   return p;
@@ -269,7 +295,11 @@ char *ipcbuf_get_write_ahead(ipcbuf_t *id, unsigned ahead)
   ipcsync_t *s = id->sync;
   if ((uint64_t)ahead + 1 > s->nbufs) return NULL;
   lock(s);
-  while (s->w_count + ahead - s->r_count >= s->nbufs) pthread_cond_wait(&s->cv, &s->mtx);
+  while (s->w_count + ahead - s->r_count >= s->nbufs)
+    if (wait_change(s) < 0) {
+      unlock(s);
+      return NULL;
+    }
   char *p = id->buffer[(s->w_count + ahead) % s->nbufs];
   unlock(s);
   return p;
@@ -304,7 +334,11 @@ char *ipcbuf_get_next_read(ipcbuf_t *id, uint64_t *bytes)
       if (bytes) *bytes = 0;
       return NULL;
     }
-    pthread_cond_wait(&s->cv, &s->mtx);
+    if (wait_change(s) < 0) {
+      unlock(s);
+      if (bytes) *bytes = 0;
+      return NULL;
+    }
   }
   const uint64_t i = s->r_count % s->nbufs;
   id->last_read_bytes = s->fill[i];

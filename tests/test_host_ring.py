@@ -234,3 +234,16 @@ def test_ring_is_reusable_for_a_second_observation(tmp_path):
             assert src.read_bytes()[4096:] == (tmp_path / name).read_bytes()[4096:]
     finally:
         run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", key)
+
+
+def test_waiters_notice_a_destroyed_ring(tmp_path):
+    """A reader blocked on an empty ring must end when the ring is destroyed under it
+    (no orphan processes after a crashed or torn-down pipeline)."""
+    key = "%x" % _key()
+    run(os.path.join(BIN, "paf_dada_db"), "-k", key, "-b", str(FRAME), "-n", "2")
+    reader = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", key, "-D", str(tmp_path), "-f", "o.dada", "-W"],
+                              stderr=subprocess.PIPE)
+    time.sleep(0.3)
+    assert reader.poll() is None                      # blocked waiting for a header
+    run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", key)
+    assert reader.wait(timeout=10) != 0               # woke up, reported "no header", exited
