@@ -247,3 +247,28 @@ def test_waiters_notice_a_destroyed_ring(tmp_path):
     assert reader.poll() is None                      # blocked waiting for a header
     run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", key)
     assert reader.wait(timeout=10) != 0               # woke up, reported "no header", exited
+
+
+def test_ascii_header_property_roundtrip(dada):
+    """Random set/get sequences: the last value set for a key is the value read, other keys keep theirs."""
+    from hypothesis import given, settings, strategies as st
+
+    keys = st.sampled_from(["UTC_START", "FREQ", "BW", "NCHAN", "TSAMP", "SOURCE", "XKEY", "Y2", "BYTES_PER_SECOND"])
+    vals = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCDEFXYZ0123456789.-:+_", min_size=1, max_size=40)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(keys, vals), min_size=1, max_size=25))
+    def check(ops):
+        buf = ctypes.create_string_buffer(open(HDR, "rb").read(), 4096)
+        model = {}
+        for k, v in ops:
+            assert dada.ascii_header_set(buf, k.encode(), b"%s", v.encode()) == 0
+            model[k] = v
+        out = ctypes.create_string_buffer(128)
+        for k, v in model.items():
+            assert dada.ascii_header_get(buf, k.encode(), b"%127s", out) == 1
+            assert out.value.decode() == v
+        assert dada.ascii_header_get(buf, b"INSTRUMENT", b"%127s", out) == 1 and out.value == b"PAF-BMF"
+        assert len(buf.value) < 4096
+
+    check()
