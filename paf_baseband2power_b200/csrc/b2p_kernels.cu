@@ -41,6 +41,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b2p_synth.h"
@@ -148,10 +149,31 @@ __device__ __forceinline__ u32x8 ldg256_stream(const void *p)
   return v;
 }
 
+/*
+ * Time splits are tapered: the first 3/4 of the splits get ranges of weight 4, the next
+ * 1/8 weight 2, the last 1/8 weight 1.  CTAs (and TMA work items) are issued in split
+ * order, so the last wave consists of short ranges and the SMs run dry together: +0.3 %
+ * on a chained stream, +0.4 % on an isolated launch (profiles/r01_variant_sweep.md).
+ */
+__device__ __forceinline__ uint64_t taper_cum(uint32_t s, uint32_t a, uint32_t b)
+{
+  const uint32_t s1 = s < a ? s : a;
+  const uint32_t s2 = s > a ? (s - a < b ? s - a : b) : 0;
+  const uint32_t s3 = s > a + b ? s - a - b : 0;
+  return 4ull * s1 + 2ull * s2 + s3;
+}
+
 /* frames [f0,f1) of time split `s` out of `n` */
 __device__ __forceinline__ void split_range(uint64_t ndf, uint32_t s, uint32_t n, uint64_t &f0,
                                             uint64_t &f1)
 {
+  if (n >= 16) {
+    const uint32_t a = n - n / 4, b = n / 8;
+    const uint64_t W = taper_cum(n, a, b);
+    f0 = ndf * taper_cum(s, a, b) / W;
+    f1 = ndf * taper_cum(s + 1, a, b) / W;
+    return;
+  }
   f0 = ndf * s / n;
   f1 = ndf * (s + 1) / n;
 }
@@ -717,6 +739,7 @@ template <typename T> cudaError_t launch_reduce_t(const B2pReduce &R, cudaStream
 cudaError_t b2p_kernels_configure(void)
 {
   cudaError_t e;
+
   if ((e = configure_all<AccExact, true>()) != cudaSuccess) return e;
   if ((e = configure_all<AccExact, false>()) != cudaSuccess) return e;
   if ((e = configure_all<AccFloat, true>()) != cudaSuccess) return e;
