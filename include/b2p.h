@@ -100,6 +100,8 @@ const char *b2p_last_error(const b2p_ctx *ctx);
  * allowed to start reading its input while the context's previous kernel is
  * still finishing (programmatic dependent launch) — so the input must be
  * complete when the call is made (synchronise the producer first).
+ * On a caller's stream, accumulate_device + finish_device neither synchronise nor
+ * allocate, so the pair can be captured into a CUDA graph and replayed.
  */
 int b2p_accumulate_device(b2p_ctx *ctx, const void *const *dptrs, uint64_t ndf, void *stream);
 

@@ -37,8 +37,8 @@ struct b2p_ctx {
   void *partials;
   float *out_dev;
   float *out_pinned;
-  /* ticket counters of the persistent (TMA) kernel: one zeroed counter per launch,
-     re-zeroed half a ring at a time, far away from the ones in use */
+  /* ticket counters of the persistent (TMA) kernel: a ring of counters, one per fused
+     launch; the reduce kernel that follows a launch puts its counter back to zero */
   unsigned int *tickets;
   uint64_t fused_seq;
   /* host-path staging */
@@ -56,6 +56,7 @@ struct b2p_ctx {
   B2pSlots pend_slots;
   int pend_nsplit;
   cudaStream_t pend_stream;
+  unsigned int *pend_ticket;
   char err[512];
 };
 
@@ -214,6 +215,7 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   c->pending = 0;
   c->pend_nsplit = 0;
   c->pend_stream = NULL;
+  c->pend_ticket = NULL;
   c->nbufs = 0;
   c->acc = c->partials = NULL;
   c->out_dev = c->out_pinned = NULL;
@@ -307,6 +309,7 @@ static int launch_reduce(b2p_ctx *c, int finish, float *out, cudaStream_t st)
   R.acc = c->acc;
   R.out = out;
   R.scale = c->p.scale;
+  R.ticket = c->pending ? c->pend_ticket : NULL;
   CK(c, b2p_launch_reduce(R, st));
   c->pending = 0;
   c->launches += 1;
@@ -360,15 +363,9 @@ static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, i
   if (ns > (uint64_t)c->nsplit) ns = (uint64_t)c->nsplit;
   L.nsplit = (int)ns;
 
-  /* a fresh ticket counter per launch; when half the ring has been used, re-zero the
-     other half's predecessor block (stream-ordered, 2048 launches away from any use) */
+  /* a counter of its own for every launch in flight (the ring is far longer than any chain) */
   const uint64_t seq = c->fused_seq++;
   L.ticket = c->tickets + (seq % B2P_NTICKETS);
-  if (seq && seq % (B2P_NTICKETS / 2) == 0) {
-    const size_t half = (size_t)(((seq / (B2P_NTICKETS / 2)) + 1) % 2) * (B2P_NTICKETS / 2);
-    if (st != c->compute) CK(c, cudaStreamSynchronize(c->compute));
-    CK(c, cudaMemsetAsync(c->tickets + half, 0, (B2P_NTICKETS / 2) * sizeof(unsigned int), st));
-  }
 
   cudaEvent_t e0 = NULL, e1 = NULL;
   if (c->timing) {
@@ -388,6 +385,7 @@ static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, i
   c->pending = 1;
   c->pend_nsplit = L.nsplit;
   c->pend_stream = st;
+  c->pend_ticket = L.ticket;
   for (int i = 0; i < B2P_MAX_BEAMS; ++i) c->pend_slots.lb[i] = -1;
   for (int b = 0; b < n; ++b) c->pend_slots.lb[L.beams.slot[b]] = b;
   return B2P_OK;

@@ -561,10 +561,14 @@ template <typename T, bool FINISH>
 __global__ void __launch_bounds__(256)
 b2p_reduce_k(const B2pSlots slots, const uint32_t nrows, const uint32_t nsplit,
              const uint32_t nchan, const T *__restrict__ partials, T *__restrict__ acc,
-             float *__restrict__ out, const float scale)
+             float *__restrict__ out, const float scale, unsigned int *__restrict__ ticket)
 {
   pdl_release_dependents();
   pdl_wait_predecessor();
+  /* the fused launch this kernel follows is complete: its work-item counter goes back to
+     zero, so the same counter is clean when the slot comes round again or when a captured
+     CUDA graph containing the pair is replayed */
+  if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= nrows * nchan) return;
   const uint32_t row = w / nchan, k = w % nchan;
@@ -729,10 +733,10 @@ template <typename T> cudaError_t launch_reduce_t(const B2pReduce &R, cudaStream
   if (R.finish)
     return launch_k(b2p_reduce_k<T, true>, grid, dim3(256), 0, st, R.pdl != 0, R.slots,
                     (uint32_t)R.nrows, (uint32_t)R.nsplit, (uint32_t)R.nchan,
-                    (const T *)R.partials, (T *)R.acc, R.out, R.scale);
+                    (const T *)R.partials, (T *)R.acc, R.out, R.scale, R.ticket);
   return launch_k(b2p_reduce_k<T, false>, grid, dim3(256), 0, st, R.pdl != 0, R.slots,
                   (uint32_t)R.nrows, (uint32_t)R.nsplit, (uint32_t)R.nchan, (const T *)R.partials,
-                  (T *)R.acc, R.out, R.scale);
+                  (T *)R.acc, R.out, R.scale, R.ticket);
 }
 } /* namespace */
 

@@ -62,6 +62,7 @@ struct B2pReduce {
   void *acc;
   float *out;
   float scale;
+  unsigned int *ticket; /* counter of the pending fused launch, reset here (NULL: none) */
 };
 
 cudaError_t b2p_launch_reduce(const B2pReduce &R, cudaStream_t st);

@@ -335,3 +335,35 @@ def test_float_mode_spans_calls(b2p, oracle_mod):
         st.read_sums()                      # exact-mode accessor
     dev.free()
     st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cuda_graph_capture_and_replay(b2p, oracle_mod, kernel):
+    """The hot path captured once into a CUDA graph (fused + finish kernel, PDL edge included) and
+    replayed on new data: no host-side state is needed between replays (the TMA kernel's work
+    counter is put back by the reduce kernel)."""
+    torch = pytest.importorskip("torch")
+    g = oracle_mod.Geometry()
+    ndf = 96
+    blocks = [oracle_mod.synth_fill(ndf, seed=800 + i, mode=i % 2) for i in range(3)]
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(b)) for b in blocks]
+    s = torch.cuda.Stream()
+    buf = torch.from_numpy(blocks[0]).cuda()
+    out = torch.zeros(g.nchan, dtype=torch.float32, device="cuda")
+    st = b2p.Baseband2Power(kernel=kernel)
+    st.accumulate_device([buf], ndf, s.cuda_stream)          # warm-up outside the capture
+    st.finish_device(out, s.cuda_stream)
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        st.accumulate_device([buf], ndf, torch.cuda.current_stream().cuda_stream)
+        st.finish_device(out, torch.cuda.current_stream().cuda_stream)
+    for rep in range(6):
+        i = rep % 3
+        buf.copy_(torch.from_numpy(blocks[i]).cuda())
+        out.zero_()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want[i].view(np.uint32)), (kernel, rep)
+    st.close()
