@@ -404,12 +404,16 @@ def main():
             times.append(time.perf_counter() - t0)
             if time.perf_counter() - t_begin > 10.0 or len(times) >= 200:
                 break
+        t0 = time.perf_counter()                      # one single-thread pass, for the per-core figure
+        oracle.accumulate(host, ndf, og, L=L)
+        t_single = time.perf_counter() - t0
         want = oracle.finish(sums, 1.0)
         parity = bool(np.array_equal(want.view(np.uint32), check_against.view(np.uint32)))
         med = statistics.median(times)
         cpu = {"value": round(blk / med / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{len(times)} passes over 1 beam-integration ({blk} B) in host RAM, median; best {round(blk / min(times) / 1e9, 3)} GB/s",
                "realtime_factor": round(g.t_integration_s * ndf / 8192 / med, 3),
+               "single_thread_GBps": round(blk / t_single / 1e9, 3),
                "note": "reference kernel absent (kernel.cu:1-7): C port of the specification, gcc -O3 -march=native -fopenmp"}
         if not parity:
             raise SystemExit("bench.py: GPU spectrum differs from the CPU oracle — number withheld")
