@@ -291,8 +291,7 @@ def main():
     torch.cuda.synchronize()
 
     def step(i):
-        st.accumulate_device(ptrs[i % nrot], ndf, None)
-        st.finish_device(out_dev, None)
+        st.integrate_device(ptrs[i % nrot], ndf, out_dev, None)   # ONE launch per integration
 
     sampler = ClockSampler(local)
     for i in range(args.warmup):
@@ -339,8 +338,7 @@ def main():
         ste = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel)
 
         def e2e_step(i):
-            ste.accumulate_host(pinned[i % hrot], ndf)
-            sp = ste.finish()                       # D2H of the spectra inside the timed region
+            sp = ste.integrate_host(pinned[i % hrot], ndf)   # H2D pieces + kernels + D2H of the spectra
             if world > 1:                           # the only cross-rank traffic of the path
                 allsp = gather_spectra(sp, my_beams, world * nbeam, group=host_pg)
                 return sp, allsp
@@ -445,15 +443,13 @@ def main():
             bp = [big.data_ptr() + b * blk for b in range(nb)]
             bx = torch.cuda.ExternalStream(sb.stream, device=torch.device("cuda", local))
             for _ in range(3):
-                sb.accumulate_device(bp, ndf, None)
-                sb.finish_device(bout, None)
+                sb.integrate_device(bp, ndf, bout, None)
             barrier()
             reps = 5
             b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             b0.record(bx)
             for _ in range(reps):
-                sb.accumulate_device(bp, ndf, None)
-                sb.finish_device(bout, None)
+                sb.integrate_device(bp, ndf, bout, None)
             b1.record(bx)
             barrier()
             bms = max_over_ranks(b0.elapsed_time(b1)) / reps

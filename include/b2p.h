@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B2P_VERSION "0.1.0"
+#define B2P_VERSION "0.2.0"
 
 /* error codes */
 #define B2P_OK        0
@@ -48,6 +48,7 @@ extern "C" {
 #define B2P_KERNEL_TMA  2 /* cp.async.bulk + mbarrier multi-stage shared-memory ring */
 
 #define B2P_MAX_BEAMS 64
+#define B2P_MAX_GROUP 16 /* GPUs one beam's channel groups can be spread over */
 
 typedef struct b2p_ctx b2p_ctx;
 
@@ -70,6 +71,14 @@ typedef struct b2p_params {
   int nsplit;           /* time splits per chunk (0 = auto from SM count) */
   uint64_t stage_ndf;   /* data frames per H2D staging piece (0 = default 256) */
   int nstage_bufs;      /* device staging buffers for the host path (0 = default 3) */
+  /* channel-group shard (north_star: "beams and channel groups shard independently"): the
+     context covers chunks [first_chunk, first_chunk + nchunk) of a stream whose data frames
+     hold nchunk_total chunks (0 = nchunk: the whole frame).  Chunks interleave inside every
+     frame (capture.c:540-542), so a shard reads rows of nchunk*7168 B at a pitch of
+     nchunk_total*7168 B (344 064).  Pointers given to accumulate calls always address frame
+     0 of the full stream — the ring block as ipcio_open_block_read returns it. */
+  int first_chunk;
+  int nchunk_total;
 } b2p_params;
 
 /* Fill *p with the reference pipeline's defaults (one beam, exact mode, scale 1). */
@@ -106,6 +115,16 @@ const char *b2p_last_error(const b2p_ctx *ctx);
 int b2p_accumulate_device(b2p_ctx *ctx, const void *const *dptrs, uint64_t ndf, void *stream);
 
 /*
+ * One whole integration in ONE kernel launch: b2p_accumulate_device of `ndf` frames and
+ * b2p_finish_device fused — the last CTA to complete each (beam, chunk) column adds the
+ * column's partial sums in fixed order to whatever earlier accumulate calls left in the
+ * accumulators, writes out_dev[b*nchan + k] and clears them.  The steady-state call of a
+ * stage whose integration is one ring block (NDF 8192, paf-baseband2power.conf:9).
+ */
+int b2p_integrate_device(b2p_ctx *ctx, const void *const *dptrs, uint64_t ndf, float *out_dev,
+                         void *stream);
+
+/*
  * Same, from host memory (a ring-buffer block returned by
  * ipcio_open_block_read): frames are cut into pieces of stage_ndf, copied
  * H2D on a copy stream into rotating staging buffers and reduced on the
@@ -116,6 +135,25 @@ int b2p_accumulate_device(b2p_ctx *ctx, const void *const *dptrs, uint64_t ndf, 
  * consumed (the caller may then release the ring block).
  */
 int b2p_accumulate_host(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf);
+
+/*
+ * b2p_accumulate_host and b2p_finish in one call: the kernel of the last staging piece
+ * closes the integration (no separate finish launch), then the spectrum is copied to
+ * out_host[nbeam*nchan].  What do_baseband2power calls when a block completes an integration.
+ */
+int b2p_integrate_host(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf, float *out_host);
+
+/*
+ * The same in asynchronous form, so that one host thread can keep several GPUs busy (one
+ * context per GPU, e.g. the channel-group shards of a beam): _async queues the copies and
+ * kernels and returns at once (finish != 0: the last piece closes the integration and the
+ * spectrum's D2H is queued; ndf == 0 with finish: close only); b2p_wait_input returns when
+ * the host blocks have been read (the ring block may be released); b2p_wait_output returns
+ * the spectrum of the integration closed last.
+ */
+int b2p_accumulate_host_async(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf, int finish);
+int b2p_wait_input(b2p_ctx *ctx);
+int b2p_wait_output(b2p_ctx *ctx, float *out_host);
 
 /*
  * Zero-copy variant: the fused kernel reads the pinned, device-mapped host
@@ -142,7 +180,9 @@ int b2p_reset(b2p_ctx *ctx);
 
 /* introspection */
 int      b2p_nchan(const b2p_ctx *ctx);            /* nchunk*nch_per_chunk */
-uint64_t b2p_frame_bytes(const b2p_ctx *ctx);      /* bytes of one data frame, all chunks */
+uint64_t b2p_frame_bytes(const b2p_ctx *ctx);      /* bytes of one data frame of this context's chunks */
+uint64_t b2p_source_frame_bytes(const b2p_ctx *ctx); /* bytes of one data frame of the source stream */
+int      b2p_first_chunk(const b2p_ctx *ctx);
 int      b2p_kernel_in_use(const b2p_ctx *ctx);    /* B2P_KERNEL_LDG / _TMA after AUTO */
 int      b2p_nsplit_in_use(const b2p_ctx *ctx);
 uint64_t b2p_launch_count(const b2p_ctx *ctx);     /* kernels launched by this context */
@@ -160,6 +200,36 @@ int      b2p_device_info(int device, char *name, size_t name_len, int *sm_count,
  */
 int b2p_set_timing(b2p_ctx *ctx, int enabled);
 int b2p_fused_time_ms(b2p_ctx *ctx, double *sum_ms, uint64_t *launches);
+
+/*
+ * Channel-group sharding of beam streams over several GPUs (SURVEY §8e "secondary";
+ * one GPU per stage process in the reference, paf_baseband2power.cu:23-26, so a beam
+ * there can never use more than one host link).  A group owns one context per GPU;
+ * GPU i covers nchunks[i] consecutive chunks (sum = params.nchunk; 0 = GPU unused), the
+ * split typically made proportional to each GPU's host-link rate.  Calls take the same
+ * full-frame host blocks as b2p_accumulate_host; every GPU copies only its own chunk
+ * columns (strided H2D) and the spectra come back as one [nbeam][nchan] array.  Issue on
+ * all GPUs first, wait afterwards: one host thread drives all links.
+ */
+typedef struct b2p_group b2p_group;
+int  b2p_group_create(b2p_group **out, const b2p_params *params, const int *devices,
+                      const int *nchunks, int ndev);
+void b2p_group_destroy(b2p_group *g);
+int  b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf);
+int  b2p_group_integrate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, float *out_host);
+int  b2p_group_finish(b2p_group *g, float *out_host);
+int  b2p_group_reset(b2p_group *g);
+int  b2p_group_size(const b2p_group *g);                  /* shards with >= 1 chunk */
+b2p_ctx *b2p_group_ctx(const b2p_group *g, int i);
+int  b2p_group_shard(const b2p_group *g, int i, int *device, int *first_chunk, int *nchunk);
+const char *b2p_group_last_error(const b2p_group *g);
+
+/* Pinned host -> device copy rate of each listed GPU with all of them copying at once
+   (`reps` copies of `bytes` each): the link weights for b2p_split_chunks. */
+int b2p_probe_h2d(const int *devices, int n, size_t bytes, int reps, double *gbps_out);
+/* Split nchunk chunks over n parts in proportion to weights (NULL = equal), largest
+   remainder; counts[] sums to nchunk exactly. */
+int b2p_split_chunks(const double *weights, int n, int nchunk, int *counts);
 
 /* host / device memory helpers (for ring registration, tests and the bench) */
 int b2p_host_alloc(void **p, size_t bytes);        /* pinned + mapped */

@@ -8,14 +8,15 @@ package is the thin ctypes mirror of that ABI.
 """
 from .geometry import Geometry, BMF  # noqa: F401
 
-__all__ = ["Geometry", "BMF", "Baseband2Power", "PinnedBuffer", "DeviceBuffer"]
+__all__ = ["Geometry", "BMF", "Baseband2Power", "ShardGroup", "PinnedBuffer", "DeviceBuffer"]
 
 
 def __getattr__(name):
     # the ABI binding is imported lazily so that `import paf_baseband2power_b200`
     # works for host-only helpers; using the stage without libb2p.so raises.
     if name in ("Baseband2Power", "PinnedBuffer", "DeviceBuffer", "B2pError", "device_count",
-                "device_info", "device_sync", "selftest_unpack"):
+                "device_info", "device_sync", "selftest_unpack", "ShardGroup", "probe_h2d",
+                "split_chunks"):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

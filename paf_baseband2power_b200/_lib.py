@@ -19,6 +19,7 @@ B2P_OK, B2P_EINVAL, B2P_ECUDA, B2P_ENOMEM, B2P_ESTATE = 0, 1, 2, 3, 4
 MODE_EXACT, MODE_FLOAT = 0, 1
 KERNEL_AUTO, KERNEL_LDG, KERNEL_TMA = 0, 1, 2
 MAX_BEAMS = 64
+MAX_GROUP = 16
 
 
 class B2pParams(Structure):
@@ -27,6 +28,7 @@ class B2pParams(Structure):
         ("device_id", c_int), ("nchunk", c_int), ("nch_per_chunk", c_int), ("nsamp_df", c_int),
         ("big_endian", c_int), ("scale", c_float), ("mode", c_int), ("nbeam", c_int),
         ("kernel", c_int), ("nsplit", c_int), ("stage_ndf", c_uint64), ("nstage_bufs", c_int),
+        ("first_chunk", c_int), ("nchunk_total", c_int),
     ]
 
 
@@ -37,7 +39,12 @@ SYMBOLS = {
     "b2p_destroy": (None, [c_void_p]),
     "b2p_last_error": (c_char_p, [c_void_p]),
     "b2p_accumulate_device": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p]),
+    "b2p_integrate_device": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p, c_void_p]),
     "b2p_accumulate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64]),
+    "b2p_integrate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p]),
+    "b2p_accumulate_host_async": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_int]),
+    "b2p_wait_input": (c_int, [c_void_p]),
+    "b2p_wait_output": (c_int, [c_void_p, c_void_p]),
     "b2p_accumulate_host_mapped": (c_int, [c_void_p, POINTER(c_void_p), c_uint64]),
     "b2p_finish": (c_int, [c_void_p, c_void_p]),
     "b2p_finish_device": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -45,6 +52,8 @@ SYMBOLS = {
     "b2p_reset": (c_int, [c_void_p]),
     "b2p_nchan": (c_int, [c_void_p]),
     "b2p_frame_bytes": (c_uint64, [c_void_p]),
+    "b2p_source_frame_bytes": (c_uint64, [c_void_p]),
+    "b2p_first_chunk": (c_int, [c_void_p]),
     "b2p_kernel_in_use": (c_int, [c_void_p]),
     "b2p_nsplit_in_use": (c_int, [c_void_p]),
     "b2p_launch_count": (c_uint64, [c_void_p]),
@@ -55,6 +64,18 @@ SYMBOLS = {
                                 POINTER(c_int), POINTER(c_uint64)]),
     "b2p_set_timing": (c_int, [c_void_p, c_int]),
     "b2p_fused_time_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_uint64)]),
+    "b2p_group_create": (c_int, [POINTER(c_void_p), POINTER(B2pParams), POINTER(c_int), POINTER(c_int), c_int]),
+    "b2p_group_destroy": (None, [c_void_p]),
+    "b2p_group_accumulate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64]),
+    "b2p_group_integrate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p]),
+    "b2p_group_finish": (c_int, [c_void_p, c_void_p]),
+    "b2p_group_reset": (c_int, [c_void_p]),
+    "b2p_group_size": (c_int, [c_void_p]),
+    "b2p_group_ctx": (c_void_p, [c_void_p, c_int]),
+    "b2p_group_shard": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "b2p_group_last_error": (c_char_p, [c_void_p]),
+    "b2p_probe_h2d": (c_int, [POINTER(c_int), c_int, c_size_t, c_int, POINTER(c_double)]),
+    "b2p_split_chunks": (c_int, [POINTER(c_double), c_int, c_int, POINTER(c_int)]),
     "b2p_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),
     "b2p_host_free": (c_int, [c_void_p]),
     "b2p_host_register": (c_int, [c_void_p, c_size_t]),

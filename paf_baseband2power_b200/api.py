@@ -148,7 +148,7 @@ class Baseband2Power:
     def __init__(self, device_id: int = 0, nbeam: int = 1, nchunk: int = 48, nch_per_chunk: int = 7,
                  nsamp_df: int = 128, big_endian: bool = True, scale: float = 1.0,
                  mode: str = "exact", kernel: str = "auto", nsplit: int = 0, stage_ndf: int = 0,
-                 nstage_bufs: int = 0):
+                 nstage_bufs: int = 0, first_chunk: int = 0, nchunk_total: int = 0):
         self._lib = _lib.load()
         p = B2pParams()
         self._lib.b2p_default_params(byref(p))
@@ -157,12 +157,14 @@ class Baseband2Power:
         p.big_endian, p.scale = int(big_endian), scale
         p.mode, p.kernel = _MODES[mode], _KERNELS[kernel]
         p.nsplit, p.stage_ndf, p.nstage_bufs = nsplit, stage_ndf, nstage_bufs
+        p.first_chunk, p.nchunk_total = first_chunk, nchunk_total
         ctx = c_void_p()
         _check(self._lib.b2p_create(byref(ctx), byref(p)))
         self._ctx = ctx
         self.nbeam = nbeam
         self.nchan = self._lib.b2p_nchan(ctx)
         self.frame_bytes = self._lib.b2p_frame_bytes(ctx)
+        self.source_frame_bytes = self._lib.b2p_source_frame_bytes(ctx)
         self.mode = mode
 
     # -- properties ---------------------------------------------------------
@@ -202,9 +204,9 @@ class Baseband2Power:
             n = b.nbytes if hasattr(b, "nbytes") else None
             if n is None:
                 raise ValueError("ndf is required when passing raw pointers")
-            if n % self.frame_bytes:
+            if n % self.source_frame_bytes:
                 raise ValueError("host block is not a whole number of data frames")
-            sizes.add(n // self.frame_bytes)
+            sizes.add(n // self.source_frame_bytes)
         if len(sizes) != 1:
             raise ValueError("all beams must supply the same number of frames")
         return sizes.pop()
@@ -213,6 +215,32 @@ class Baseband2Power:
         ndf = self._host_ndf(blocks, ndf)
         arr = self._ptr_array(blocks, _host_ptr)
         _check(self._lib.b2p_accumulate_host(self._ctx, arr, ndf), self._ctx)
+
+    def integrate_device(self, dptrs: Sequence, ndf: int, out_dev, stream: int | None = None):
+        """accumulate_device + finish_device in one kernel launch."""
+        arr = self._ptr_array(dptrs, _dev_ptr)
+        _check(self._lib.b2p_integrate_device(self._ctx, arr, ndf, _dev_ptr(out_dev), stream), self._ctx)
+
+    def integrate_host(self, blocks: Sequence, ndf: int | None = None) -> np.ndarray:
+        """accumulate_host + finish: the last staging piece's kernel closes the integration."""
+        ndf = self._host_ndf(blocks, ndf)
+        arr = self._ptr_array(blocks, _host_ptr)
+        out = np.empty((self.nbeam, self.nchan), dtype=np.float32)
+        _check(self._lib.b2p_integrate_host(self._ctx, arr, ndf, out.ctypes.data), self._ctx)
+        return out
+
+    def accumulate_host_async(self, blocks: Sequence, ndf: int | None = None, finish: bool = False):
+        ndf = self._host_ndf(blocks, ndf)
+        arr = self._ptr_array(blocks, _host_ptr)
+        _check(self._lib.b2p_accumulate_host_async(self._ctx, arr, ndf, int(finish)), self._ctx)
+
+    def wait_input(self):
+        _check(self._lib.b2p_wait_input(self._ctx), self._ctx)
+
+    def wait_output(self) -> np.ndarray:
+        out = np.empty((self.nbeam, self.nchan), dtype=np.float32)
+        _check(self._lib.b2p_wait_output(self._ctx, out.ctypes.data), self._ctx)
+        return out
 
     def accumulate_host_mapped(self, blocks: Sequence, ndf: int | None = None):
         ndf = self._host_ndf(blocks, ndf)
@@ -249,6 +277,105 @@ class Baseband2Power:
         if getattr(self, "_ctx", None):
             self._lib.b2p_destroy(self._ctx)
             self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def probe_h2d(devices: Sequence[int], nbytes: int = 256 << 20, reps: int = 4) -> list[float]:
+    """Pinned host->device GB/s of every listed GPU, all copying at once."""
+    n = len(devices)
+    out = (c_double * n)()
+    _check(_lib.load().b2p_probe_h2d((c_int * n)(*devices), n, nbytes, reps, out))
+    return list(out)
+
+
+def split_chunks(weights: Sequence[float] | None, n: int, nchunk: int = 48) -> list[int]:
+    """nchunk chunks over n GPUs in proportion to `weights` (largest remainder)."""
+    counts = (c_int * n)()
+    w = (c_double * n)(*weights) if weights is not None else None
+    _check(_lib.load().b2p_split_chunks(w, n, nchunk, counts))
+    return list(counts)
+
+
+class ShardGroup:
+    """Beam streams spread over several GPUs by channel group (include/b2p.h b2p_group_*):
+    GPU devices[i] covers nchunks[i] consecutive chunks of every data frame."""
+
+    def __init__(self, devices: Sequence[int], nchunks: Sequence[int], nbeam: int = 1, nchunk: int = 48,
+                 nch_per_chunk: int = 7, nsamp_df: int = 128, big_endian: bool = True,
+                 scale: float = 1.0, mode: str = "exact", kernel: str = "auto", nstage_bufs: int = 0):
+        self._lib = _lib.load()
+        p = B2pParams()
+        self._lib.b2p_default_params(byref(p))
+        p.nbeam, p.nchunk, p.nch_per_chunk, p.nsamp_df = nbeam, nchunk, nch_per_chunk, nsamp_df
+        p.big_endian, p.scale = int(big_endian), scale
+        p.mode, p.kernel, p.nstage_bufs = _MODES[mode], _KERNELS[kernel], nstage_bufs
+        n = len(devices)
+        if len(nchunks) != n:
+            raise ValueError("one chunk count per device")
+        g = c_void_p()
+        rc = self._lib.b2p_group_create(byref(g), byref(p), (c_int * n)(*devices), (c_int * n)(*nchunks), n)
+        _check(rc)
+        self._g = g
+        self.nbeam, self.nchan = nbeam, nchunk * nch_per_chunk
+        self.source_frame_bytes = nchunk * nch_per_chunk * nsamp_df * 8
+
+    def _check(self, rc):
+        if rc:
+            msg = self._lib.b2p_group_last_error(self._g)
+            raise B2pError(rc, msg.decode() if msg else "")
+
+    @property
+    def shards(self) -> list[tuple[int, int, int]]:
+        """(device, first_chunk, nchunk) of every shard that holds at least one chunk."""
+        out = []
+        for i in range(self._lib.b2p_group_size(self._g)):
+            d, f, n = c_int(), c_int(), c_int()
+            self._lib.b2p_group_shard(self._g, i, byref(d), byref(f), byref(n))
+            out.append((d.value, f.value, n.value))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return sum(self._lib.b2p_launch_count(self._lib.b2p_group_ctx(self._g, i))
+                   for i in range(self._lib.b2p_group_size(self._g)))
+
+    def _ptrs(self, blocks):
+        ptrs = [_host_ptr(x) for x in blocks]
+        if len(ptrs) != self.nbeam:
+            raise ValueError(f"expected {self.nbeam} beam pointers, got {len(ptrs)}")
+        return (c_void_p * self.nbeam)(*ptrs)
+
+    def accumulate_host(self, blocks: Sequence, ndf: int):
+        self._check(self._lib.b2p_group_accumulate_host(self._g, self._ptrs(blocks), ndf))
+
+    def integrate_host(self, blocks: Sequence, ndf: int) -> np.ndarray:
+        out = np.empty((self.nbeam, self.nchan), dtype=np.float32)
+        self._check(self._lib.b2p_group_integrate_host(self._g, self._ptrs(blocks), ndf, out.ctypes.data))
+        return out
+
+    def finish(self) -> np.ndarray:
+        out = np.empty((self.nbeam, self.nchan), dtype=np.float32)
+        self._check(self._lib.b2p_group_finish(self._g, out.ctypes.data))
+        return out
+
+    def reset(self):
+        self._check(self._lib.b2p_group_reset(self._g))
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.b2p_group_destroy(self._g)
+            self._g = None
 
     def __enter__(self):
         return self

@@ -24,21 +24,27 @@
 
 struct b2p_ctx {
   b2p_params p;
-  int nchan;
-  uint64_t frame_bytes;
+  int nchan;            /* channels this context produces: nchunk * nch_per_chunk */
+  uint64_t pkt_bytes;   /* payload of one packet (one frame of one chunk) */
+  uint64_t frame_bytes; /* one data frame of this context's chunks (compact) */
+  uint64_t src_pitch;   /* one data frame of the source stream: nchunk_total * pkt_bytes */
+  uint64_t src_offset;  /* first_chunk * pkt_bytes */
   int sm_count;
-  int kernel; /* resolved */
-  int nsplit; /* resolved */
+  int kernel;  /* resolved */
+  int nsplit;  /* resolved: splits of a full-length launch */
+  int split_base; /* smallest split count that fills whole waves */
   int variant; /* tuning variant, B2P_VARIANT env (experiments) */
   int no_early; /* B2P_NO_EARLY=1: never start a fused kernel before its predecessor ends */
+  int calib;
   size_t acc_elem;
   cudaStream_t compute, copy;
   void *acc;
   void *partials;
   float *out_dev;
   float *out_pinned;
-  /* ticket counters of the persistent (TMA) kernel: a ring of counters, one per fused
-     launch; the reduce kernel that follows a launch puts its counter back to zero */
+  unsigned int *colcnt; /* per (launch beam, column) arrival counters; zero between launches */
+  /* ticket counters of the persistent (TMA) kernel: a ring, one per fused launch in flight;
+     a launch leaves its counter at zero (the last draw past the end resets it) */
   unsigned int *tickets;
   uint64_t fused_seq;
   /* host-path staging */
@@ -46,17 +52,15 @@ struct b2p_ctx {
   void *stage[B2P_MAX_STAGE_BUFS];
   cudaEvent_t copied[B2P_MAX_STAGE_BUFS], consumed[B2P_MAX_STAGE_BUFS];
   uint64_t pieces; /* pieces issued so far over the context's life */
+  int out_queued;  /* a D2H of the spectrum is queued on the compute stream */
   /* per-launch timing */
   int timing;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used;
   uint64_t launches;
-  /* partial sums of the last fused launch not yet folded into acc */
-  int pending;
-  B2pSlots pend_slots;
-  int pend_nsplit;
-  cudaStream_t pend_stream;
-  unsigned int *pend_ticket;
+  /* stream of the most recent launch: a launch on another stream is ordered behind it */
+  cudaStream_t last_stream;
+  cudaEvent_t xev;
   char err[512];
 };
 
@@ -110,6 +114,8 @@ void b2p_default_params(b2p_params *p)
   p->nsplit = 0;
   p->stage_ndf = 0;
   p->nstage_bufs = 0;
+  p->first_chunk = 0;
+  p->nchunk_total = 0;
 }
 
 const char *b2p_last_error(const b2p_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
@@ -151,8 +157,9 @@ static int resolve_kernel(const b2p_params *p)
   return k;
 }
 
-static int resolve_nsplit(const b2p_params *p, int kernel, int sm_count)
+static int resolve_nsplit(const b2p_params *p, int kernel, int sm_count, int *base_out)
 {
+  *base_out = 0;
   if (p->nsplit > 0) return p->nsplit > 1024 ? 1024 : p->nsplit;
   /* base = smallest split count that makes the grid a whole number of waves;
      LDG: 4 CTAs/SM and ~37 frames per CTA measured best (18 waves for one beam). */
@@ -167,6 +174,7 @@ static int resolve_nsplit(const b2p_params *p, int kernel, int sm_count)
     target = 222; /* 8192 frames / 222 = 37 frames per CTA */
   }
   const unsigned base = slots / gcd_u(slots, units); /* smallest n with n*units % slots == 0 */
+  *base_out = (int)(base > 1024 ? 1024 : base);
   unsigned k = (target + base / 2) / base;
   if (k < 1) k = 1;
   unsigned n = base * k;
@@ -190,6 +198,9 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
     FAIL(NULL, B2P_EINVAL, "b2p_create: unknown mode");
   if (p->kernel < B2P_KERNEL_AUTO || p->kernel > B2P_KERNEL_TMA)
     FAIL(NULL, B2P_EINVAL, "b2p_create: unknown kernel variant");
+  const int ntotal = p->nchunk_total > 0 ? p->nchunk_total : p->nchunk;
+  if (p->first_chunk < 0 || p->first_chunk + p->nchunk > ntotal)
+    FAIL(NULL, B2P_EINVAL, "b2p_create: chunk range [first_chunk, first_chunk+nchunk) exceeds nchunk_total");
 
   int ndev = 0;
   CK(NULL, cudaGetDeviceCount(&ndev));
@@ -204,24 +215,27 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   if (!c) FAIL(NULL, B2P_ENOMEM, "b2p_create: out of host memory");
   c->p = *p;
   c->p.device_id = dev;
+  c->p.nchunk_total = ntotal;
   c->nchan = p->nchunk * p->nch_per_chunk;
-  c->frame_bytes = (uint64_t)p->nchunk * p->nsamp_df * p->nch_per_chunk * 8u;
+  c->pkt_bytes = (uint64_t)p->nsamp_df * p->nch_per_chunk * 8u;
+  c->frame_bytes = (uint64_t)p->nchunk * c->pkt_bytes;
+  c->src_pitch = (uint64_t)ntotal * c->pkt_bytes;
+  c->src_offset = (uint64_t)p->first_chunk * c->pkt_bytes;
   c->acc_elem = 8;
   c->err[0] = 0;
   c->pieces = 0;
+  c->out_queued = 0;
   c->timing = 0;
   c->ev_used = 0;
   c->launches = 0;
-  c->pending = 0;
-  c->pend_nsplit = 0;
-  c->pend_stream = NULL;
-  c->pend_ticket = NULL;
   c->nbufs = 0;
   c->acc = c->partials = NULL;
   c->out_dev = c->out_pinned = NULL;
-  c->tickets = NULL;
+  c->tickets = c->colcnt = NULL;
   c->fused_seq = 0;
   c->compute = c->copy = NULL;
+  c->last_stream = NULL;
+  c->xev = NULL;
   for (int i = 0; i < B2P_MAX_STAGE_BUFS; ++i) {
     c->stage[i] = NULL;
     c->copied[i] = c->consumed[i] = NULL;
@@ -241,18 +255,23 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
   CKC(b2p_kernels_configure());
   c->kernel = resolve_kernel(p);
-  c->nsplit = resolve_nsplit(p, c->kernel, c->sm_count);
+  c->nsplit = resolve_nsplit(p, c->kernel, c->sm_count, &c->split_base);
   c->variant = getenv("B2P_VARIANT") ? atoi(getenv("B2P_VARIANT")) : 0;
   c->no_early = getenv("B2P_NO_EARLY") ? atoi(getenv("B2P_NO_EARLY")) : 0;
+  c->calib = getenv("B2P_CALIB") ? atoi(getenv("B2P_CALIB")) : 0;
   CKC(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&c->xev, cudaEventDisableTiming));
   const size_t nacc = (size_t)p->nbeam * c->nchan;
+  const size_t ncnt = (size_t)p->nbeam * p->nchunk;
   CKC(cudaMalloc(&c->acc, nacc * c->acc_elem));
   CKC(cudaMemset(c->acc, 0, nacc * c->acc_elem));
   CKC(cudaMalloc(&c->partials, nacc * (size_t)c->nsplit * c->acc_elem));
   CKC(cudaMalloc((void **)&c->out_dev, nacc * sizeof(float)));
   CKC(cudaMalloc((void **)&c->tickets, B2P_NTICKETS * sizeof(unsigned int)));
   CKC(cudaMemset(c->tickets, 0, B2P_NTICKETS * sizeof(unsigned int)));
+  CKC(cudaMalloc((void **)&c->colcnt, ncnt * sizeof(unsigned int)));
+  CKC(cudaMemset(c->colcnt, 0, ncnt * sizeof(unsigned int)));
   CKC(cudaHostAlloc((void **)&c->out_pinned, nacc * sizeof(float), cudaHostAllocDefault));
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -264,6 +283,7 @@ void b2p_destroy(b2p_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->p.device_id);
+  if (c->last_stream && c->last_stream != c->compute) cudaStreamSynchronize(c->last_stream);
   if (c->compute) cudaStreamSynchronize(c->compute);
   if (c->copy) cudaStreamSynchronize(c->copy);
   for (int i = 0; i < B2P_MAX_STAGE_BUFS; ++i) {
@@ -272,10 +292,12 @@ void b2p_destroy(b2p_ctx *c)
     if (c->consumed[i]) cudaEventDestroy(c->consumed[i]);
   }
   for (size_t i = 0; i < c->ev_pool.size(); ++i) cudaEventDestroy(c->ev_pool[i]);
+  if (c->xev) cudaEventDestroy(c->xev);
   if (c->acc) cudaFree(c->acc);
   if (c->partials) cudaFree(c->partials);
   if (c->out_dev) cudaFree(c->out_dev);
   if (c->tickets) cudaFree(c->tickets);
+  if (c->colcnt) cudaFree(c->colcnt);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->copy) cudaStreamDestroy(c->copy);
@@ -284,49 +306,53 @@ void b2p_destroy(b2p_ctx *c)
 
 int b2p_nchan(const b2p_ctx *c) { return c ? c->nchan : 0; }
 uint64_t b2p_frame_bytes(const b2p_ctx *c) { return c ? c->frame_bytes : 0; }
+uint64_t b2p_source_frame_bytes(const b2p_ctx *c) { return c ? c->src_pitch : 0; }
+int b2p_first_chunk(const b2p_ctx *c) { return c ? c->p.first_chunk : 0; }
 int b2p_kernel_in_use(const b2p_ctx *c) { return c ? c->kernel : 0; }
 int b2p_nsplit_in_use(const b2p_ctx *c) { return c ? c->nsplit : 0; }
 uint64_t b2p_launch_count(const b2p_ctx *c) { return c ? c->launches : 0; }
 void *b2p_stream(const b2p_ctx *c) { return c ? (void *)c->compute : NULL; }
 
-/* Fold the pending partial sums into the accumulators (finish=0) or emit the
-   spectrum and clear (finish=1).  One kernel either way. */
-static int launch_reduce(b2p_ctx *c, int finish, float *out, cudaStream_t st)
+/* Successive launches of a context share partial sums, counters and accumulators, so they
+   must execute in issue order.  Same stream: stream order.  Another stream: it waits for
+   everything the context has put on the stream it used last. */
+static int order_behind_last(b2p_ctx *c, cudaStream_t st)
 {
-  B2pReduce R;
-  memset(&R, 0, sizeof(R));
-  if (c->pending)
-    R.slots = c->pend_slots;
-  else
-    for (int i = 0; i < B2P_MAX_BEAMS; ++i) R.slots.lb[i] = -1;
-  R.nrows = c->p.nbeam;
-  R.nsplit = c->pending ? c->pend_nsplit : 0;
-  R.nchan = c->nchan;
-  R.mode = c->p.mode;
-  R.finish = finish;
-  R.pdl = 1;
-  R.partials = c->partials;
-  R.acc = c->acc;
-  R.out = out;
-  R.scale = c->p.scale;
-  R.ticket = c->pending ? c->pend_ticket : NULL;
-  CK(c, b2p_launch_reduce(R, st));
-  c->pending = 0;
-  c->launches += 1;
+  if (c->last_stream && c->last_stream != st) {
+    CK(c, cudaEventRecord(c->xev, c->last_stream));
+    CK(c, cudaStreamWaitEvent(st, c->xev, 0));
+  }
+  c->last_stream = st;
   return B2P_OK;
 }
 
-static int flush_pending(b2p_ctx *c, cudaStream_t st)
+/* time splits of a launch of `ndf` frames: whole waves, never fewer than ~8 frames per CTA
+   when that can be helped; a full-length launch gets the context's nsplit */
+static int splits_for(const b2p_ctx *c, uint64_t ndf)
 {
-  if (!c->pending) return B2P_OK;
-  if (c->pend_stream != st) CK(c, cudaStreamSynchronize(c->pend_stream));
-  return launch_reduce(c, 0, NULL, st);
+  uint64_t ns;
+  if (c->split_base > 0) {
+    uint64_t k = ndf / (8u * (uint64_t)c->split_base);
+    const uint64_t kmax = (uint64_t)(c->nsplit / c->split_base);
+    if (k > kmax) k = kmax;
+    if (k < 1) k = 1;
+    ns = k * (uint64_t)c->split_base;
+  } else {
+    ns = (uint64_t)c->nsplit; /* caller-chosen split count */
+  }
+  if (ns > ndf) ns = ndf;
+  if (ns > (uint64_t)c->nsplit) ns = (uint64_t)c->nsplit;
+  if (ns < 1) ns = 1;
+  return (int)ns;
 }
 
-/* One fused launch for `n` beams on `st`; its partial sums stay pending until the
-   next accumulate (folded into acc first) or finish (folded and converted at once). */
+/*
+ * One fused launch for `n` beams on `st`: unpack + detect + integrate `ndf` frames per beam
+ * read with frame pitch `fpitch`, then (inside the same kernel) fold the column sums into
+ * the accumulators, or — finish — emit the spectrum to `out` and clear them.
+ */
 static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, int n, uint64_t ndf,
-                        int kernel, cudaStream_t st)
+                        uint64_t fpitch, int kernel, cudaStream_t st, int finish, float *out)
 {
   B2pLaunch L;
   memset(&L, 0, sizeof(L));
@@ -338,32 +364,33 @@ static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, i
     L.beams.ptr[b] = ptrs[b];
     L.beams.slot[b] = slots ? slots[b] : b;
   }
-  int rc = flush_pending(c, st);
+  int rc = order_behind_last(c, st);
   if (rc) return rc;
   L.nbeam = n;
   L.nchunk = c->p.nchunk;
   L.nch = c->p.nch_per_chunk;
   L.nsamp = c->p.nsamp_df;
+  L.fpitch = fpitch;
   L.big_endian = c->p.big_endian;
   L.mode = c->p.mode;
   L.kernel = kernel;
   L.sm_count = c->sm_count;
   L.variant = c->variant;
-  L.calib = getenv("B2P_CALIB") ? atoi(getenv("B2P_CALIB")) : 0;
+  L.calib = c->calib;
   L.pdl = 1;
   /* Only on the context's own stream is it known that the input was complete before
      the call: there the kernel may start while its predecessor is still running. */
   L.early = (st == c->compute && !c->no_early) ? 1 : 0;
   L.ndf = ndf;
   L.partials = c->partials;
-  L.acc = c->acc;
-  /* short launches: never give a CTA fewer than 16 frames if it can be helped */
-  uint64_t ns = ndf / 16;
-  if (ns < 1) ns = 1;
-  if (ns > (uint64_t)c->nsplit) ns = (uint64_t)c->nsplit;
-  L.nsplit = (int)ns;
+  L.nsplit = splits_for(c, ndf);
+  L.fold.acc = c->acc;
+  L.fold.out = out;
+  L.fold.colcnt = c->colcnt;
+  L.fold.scale = c->p.scale;
+  L.fold.finish = finish;
 
-  /* a counter of its own for every launch in flight (the ring is far longer than any chain) */
+  /* a counter of its own for every launch that can be in flight at once */
   const uint64_t seq = c->fused_seq++;
   L.ticket = c->tickets + (seq % B2P_NTICKETS);
 
@@ -382,23 +409,43 @@ static int launch_fused(b2p_ctx *c, const void *const *ptrs, const int *slots, i
   CK(c, b2p_launch_fused(L, st));
   if (c->timing) CK(c, cudaEventRecord(e1, st));
   c->launches += 1;
-  c->pending = 1;
-  c->pend_nsplit = L.nsplit;
-  c->pend_stream = st;
-  c->pend_ticket = L.ticket;
-  for (int i = 0; i < B2P_MAX_BEAMS; ++i) c->pend_slots.lb[i] = -1;
-  for (int b = 0; b < n; ++b) c->pend_slots.lb[L.beams.slot[b]] = b;
   return B2P_OK;
+}
+
+/* the caller's pointers address frame 0 of the source stream; a shard starts first_chunk in */
+static void shard_ptrs(const b2p_ctx *c, const void *const *in, const void **out)
+{
+  for (int b = 0; b < c->p.nbeam; ++b)
+    out[b] = in[b] ? (const void *)((const unsigned char *)in[b] + c->src_offset) : NULL;
+}
+
+static int device_call(b2p_ctx *c, const void *const *dptrs, uint64_t ndf, void *stream, int finish,
+                       float *out_dev)
+{
+  if (!c) return B2P_EINVAL;
+  if (!dptrs) FAIL(c, B2P_EINVAL, "b2p_accumulate_device: NULL dptrs");
+  CK(c, cudaSetDevice(c->p.device_id));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->compute;
+  if (ndf == 0) {
+    if (!finish) return B2P_OK;
+    return b2p_finish_device(c, out_dev, stream);
+  }
+  const void *ptrs[B2P_MAX_BEAMS];
+  shard_ptrs(c, dptrs, ptrs);
+  return launch_fused(c, ptrs, NULL, c->p.nbeam, ndf, c->src_pitch, c->kernel, st, finish, out_dev);
 }
 
 int b2p_accumulate_device(b2p_ctx *c, const void *const *dptrs, uint64_t ndf, void *stream)
 {
+  return device_call(c, dptrs, ndf, stream, 0, NULL);
+}
+
+int b2p_integrate_device(b2p_ctx *c, const void *const *dptrs, uint64_t ndf, float *out_dev,
+                         void *stream)
+{
   if (!c) return B2P_EINVAL;
-  if (!dptrs) FAIL(c, B2P_EINVAL, "b2p_accumulate_device: NULL dptrs");
-  if (ndf == 0) return B2P_OK;
-  CK(c, cudaSetDevice(c->p.device_id));
-  cudaStream_t st = stream ? (cudaStream_t)stream : c->compute;
-  return launch_fused(c, dptrs, NULL, c->p.nbeam, ndf, c->kernel, st);
+  if (!out_dev) FAIL(c, B2P_EINVAL, "b2p_integrate_device: NULL output");
+  return device_call(c, dptrs, ndf, stream, 1, out_dev);
 }
 
 static int ensure_staging(b2p_ctx *c)
@@ -407,7 +454,11 @@ static int ensure_staging(b2p_ctx *c)
   int nb = c->p.nstage_bufs > 0 ? c->p.nstage_bufs : 3;
   if (nb < 2) nb = 2;
   if (nb > B2P_MAX_STAGE_BUFS) nb = B2P_MAX_STAGE_BUFS;
-  if (c->p.stage_ndf == 0) c->p.stage_ndf = 256;
+  if (c->p.stage_ndf == 0) {
+    /* ~88 MB per piece whatever the shard width: 256 frames of 48 chunks */
+    uint64_t n = 256u * (uint64_t)c->p.nchunk_total / (uint64_t)c->p.nchunk;
+    c->p.stage_ndf = n ? n : 1;
+  }
   const size_t bytes = (size_t)c->p.stage_ndf * c->frame_bytes;
   for (int i = 0; i < nb; ++i) {
     CK(c, cudaMalloc(&c->stage[i], bytes));
@@ -418,37 +469,98 @@ static int ensure_staging(b2p_ctx *c)
   return B2P_OK;
 }
 
-int b2p_accumulate_host(b2p_ctx *c, const void *const *hptrs, uint64_t ndf)
+/* queue: per beam, pieces of stage_ndf frames -> H2D (2-D when the context is a chunk-group
+   shard of wider frames) into the staging ring -> fused kernel; the last piece of a beam
+   finishes that beam's row when `finish`.  Nothing here waits for the device. */
+static int host_issue(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int finish)
 {
-  if (!c) return B2P_EINVAL;
-  if (!hptrs) FAIL(c, B2P_EINVAL, "b2p_accumulate_host: NULL hptrs");
-  for (int b = 0; b < c->p.nbeam; ++b)
-    if (!hptrs[b]) FAIL(c, B2P_EINVAL, "b2p_accumulate_host: NULL beam pointer");
-  if (ndf == 0) return B2P_OK;
+  if (ndf) {
+    if (!hptrs) FAIL(c, B2P_EINVAL, "b2p_accumulate_host: NULL hptrs");
+    for (int b = 0; b < c->p.nbeam; ++b)
+      if (!hptrs[b]) FAIL(c, B2P_EINVAL, "b2p_accumulate_host: NULL beam pointer");
+  }
   CK(c, cudaSetDevice(c->p.device_id));
+  if (ndf == 0) {
+    if (!finish) return B2P_OK;
+    int rc0 = b2p_finish_device(c, c->out_dev, c->compute);
+    if (rc0) return rc0;
+  }
   int rc = ensure_staging(c);
   if (rc) return rc;
   const uint64_t piece = c->p.stage_ndf;
-  for (int b = 0; b < c->p.nbeam; ++b) {
-    const unsigned char *src = (const unsigned char *)hptrs[b];
+  const bool compact = c->src_pitch == c->frame_bytes;
+  for (int b = 0; b < c->p.nbeam && ndf; ++b) {
+    const unsigned char *src = (const unsigned char *)hptrs[b] + c->src_offset;
     for (uint64_t f0 = 0; f0 < ndf; f0 += piece) {
       const uint64_t n = (ndf - f0 < piece) ? ndf - f0 : piece;
       const int buf = (int)(c->pieces % (uint64_t)c->nbufs);
       if (c->pieces >= (uint64_t)c->nbufs) CK(c, cudaStreamWaitEvent(c->copy, c->consumed[buf], 0));
-      CK(c, cudaMemcpyAsync(c->stage[buf], src + f0 * c->frame_bytes, n * c->frame_bytes,
-                            cudaMemcpyHostToDevice, c->copy));
+      if (compact)
+        CK(c, cudaMemcpyAsync(c->stage[buf], src + f0 * c->src_pitch, n * c->frame_bytes,
+                              cudaMemcpyHostToDevice, c->copy));
+      else /* chunks [first_chunk, +nchunk) of every frame: rows of frame_bytes, pitch src_pitch */
+        CK(c, cudaMemcpy2DAsync(c->stage[buf], c->frame_bytes, src + f0 * c->src_pitch, c->src_pitch,
+                                c->frame_bytes, n, cudaMemcpyHostToDevice, c->copy));
       CK(c, cudaEventRecord(c->copied[buf], c->copy));
       CK(c, cudaStreamWaitEvent(c->compute, c->copied[buf], 0));
       const void *ptr = c->stage[buf];
-      rc = launch_fused(c, &ptr, &b, 1, n, c->kernel, c->compute);
+      const int fin = finish && f0 + n == ndf;
+      rc = launch_fused(c, &ptr, &b, 1, n, c->frame_bytes, c->kernel, c->compute, fin, c->out_dev);
       if (rc) return rc;
       CK(c, cudaEventRecord(c->consumed[buf], c->compute));
       c->pieces++;
     }
   }
+  if (finish) {
+    const size_t bytes = (size_t)c->p.nbeam * c->nchan * sizeof(float);
+    CK(c, cudaMemcpyAsync(c->out_pinned, c->out_dev, bytes, cudaMemcpyDeviceToHost, c->compute));
+    c->out_queued = 1;
+  }
+  return B2P_OK;
+}
+
+int b2p_accumulate_host_async(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int finish)
+{
+  if (!c) return B2P_EINVAL;
+  return host_issue(c, hptrs, ndf, finish);
+}
+
+int b2p_wait_input(b2p_ctx *c)
+{
+  if (!c) return B2P_EINVAL;
+  CK(c, cudaSetDevice(c->p.device_id));
   /* every byte has left the host block once the copy stream drains */
   CK(c, cudaStreamSynchronize(c->copy));
   return B2P_OK;
+}
+
+int b2p_wait_output(b2p_ctx *c, float *out_host)
+{
+  if (!c) return B2P_EINVAL;
+  if (!out_host) FAIL(c, B2P_EINVAL, "b2p_wait_output: NULL output");
+  if (!c->out_queued) FAIL(c, B2P_ESTATE, "b2p_wait_output: no finished integration is queued");
+  CK(c, cudaSetDevice(c->p.device_id));
+  CK(c, cudaStreamSynchronize(c->compute));
+  memcpy(out_host, c->out_pinned, (size_t)c->p.nbeam * c->nchan * sizeof(float));
+  c->out_queued = 0;
+  return B2P_OK;
+}
+
+int b2p_accumulate_host(b2p_ctx *c, const void *const *hptrs, uint64_t ndf)
+{
+  if (!c) return B2P_EINVAL;
+  int rc = host_issue(c, hptrs, ndf, 0);
+  if (rc) return rc;
+  return b2p_wait_input(c);
+}
+
+int b2p_integrate_host(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, float *out_host)
+{
+  if (!c) return B2P_EINVAL;
+  if (!out_host) FAIL(c, B2P_EINVAL, "b2p_integrate_host: NULL output");
+  int rc = host_issue(c, hptrs, ndf, 1);
+  if (rc) return rc;
+  return b2p_wait_output(c, out_host); /* the compute stream runs behind the copy stream */
 }
 
 int b2p_accumulate_host_mapped(b2p_ctx *c, const void *const *hptrs, uint64_t ndf)
@@ -462,11 +574,13 @@ int b2p_accumulate_host_mapped(b2p_ctx *c, const void *const *hptrs, uint64_t nd
     if (!hptrs[b]) FAIL(c, B2P_EINVAL, "b2p_accumulate_host_mapped: NULL beam pointer");
     void *d = NULL;
     CK(c, cudaHostGetDevicePointer(&d, (void *)hptrs[b], 0));
-    dptrs[b] = d;
+    dptrs[b] = (const unsigned char *)d + c->src_offset;
   }
-  int rc = launch_fused(c, dptrs, NULL, c->p.nbeam, ndf, B2P_KERNEL_LDG, c->compute);
+  /* the kernel walks the host block itself, frame pitch = that of the source stream */
+  int rc = launch_fused(c, dptrs, NULL, c->p.nbeam, ndf, c->src_pitch, B2P_KERNEL_LDG, c->compute, 0,
+                        NULL);
   if (rc) return rc;
-  CK(c, cudaStreamSynchronize(c->compute)); /* the kernel reads the host block itself */
+  CK(c, cudaStreamSynchronize(c->compute));
   return B2P_OK;
 }
 
@@ -476,8 +590,20 @@ int b2p_finish_device(b2p_ctx *c, float *out_dev, void *stream)
   if (!out_dev) FAIL(c, B2P_EINVAL, "b2p_finish_device: NULL output");
   CK(c, cudaSetDevice(c->p.device_id));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->compute;
-  if (c->pending && c->pend_stream != st) CK(c, cudaStreamSynchronize(c->pend_stream));
-  return launch_reduce(c, 1, out_dev, st);
+  int rc = order_behind_last(c, st);
+  if (rc) return rc;
+  B2pFinish R;
+  memset(&R, 0, sizeof(R));
+  R.nrows = c->p.nbeam;
+  R.nchan = c->nchan;
+  R.mode = c->p.mode;
+  R.pdl = 1;
+  R.acc = c->acc;
+  R.out = out_dev;
+  R.scale = c->p.scale;
+  CK(c, b2p_launch_finish(R, st));
+  c->launches += 1;
+  return B2P_OK;
 }
 
 int b2p_finish(b2p_ctx *c, float *out_host)
@@ -490,6 +616,16 @@ int b2p_finish(b2p_ctx *c, float *out_host)
   CK(c, cudaMemcpyAsync(c->out_pinned, c->out_dev, bytes, cudaMemcpyDeviceToHost, c->compute));
   CK(c, cudaStreamSynchronize(c->compute));
   memcpy(out_host, c->out_pinned, bytes);
+  c->out_queued = 0;
+  return B2P_OK;
+}
+
+/* wait for everything the context has launched, wherever it launched it */
+static int drain(b2p_ctx *c)
+{
+  if (c->last_stream && c->last_stream != c->compute) CK(c, cudaStreamSynchronize(c->last_stream));
+  CK(c, cudaStreamSynchronize(c->copy));
+  CK(c, cudaStreamSynchronize(c->compute));
   return B2P_OK;
 }
 
@@ -499,13 +635,8 @@ int b2p_read_sums(b2p_ctx *c, uint64_t *sums_host)
   if (!sums_host) FAIL(c, B2P_EINVAL, "b2p_read_sums: NULL output");
   if (c->p.mode != B2P_MODE_EXACT) FAIL(c, B2P_ESTATE, "b2p_read_sums: exact mode only");
   CK(c, cudaSetDevice(c->p.device_id));
-  if (c->pending) {
-    cudaStream_t ps = c->pend_stream;
-    int rc = flush_pending(c, ps);
-    if (rc) return rc;
-    CK(c, cudaStreamSynchronize(ps));
-  }
-  CK(c, cudaStreamSynchronize(c->compute));
+  int rc = drain(c);
+  if (rc) return rc;
   CK(c, cudaMemcpy(sums_host, c->acc, (size_t)c->p.nbeam * c->nchan * 8, cudaMemcpyDeviceToHost));
   return B2P_OK;
 }
@@ -514,12 +645,12 @@ int b2p_reset(b2p_ctx *c)
 {
   if (!c) return B2P_EINVAL;
   CK(c, cudaSetDevice(c->p.device_id));
-  if (c->pending) {
-    CK(c, cudaStreamSynchronize(c->pend_stream));
-    c->pending = 0;
-  }
+  int rc = drain(c);
+  if (rc) return rc;
+  /* nothing else to put right: every launch leaves its counters (columns, TMA ticket) at zero */
   CK(c, cudaMemsetAsync(c->acc, 0, (size_t)c->p.nbeam * c->nchan * c->acc_elem, c->compute));
   CK(c, cudaStreamSynchronize(c->compute));
+  c->out_queued = 0;
   return B2P_OK;
 }
 
@@ -599,6 +730,244 @@ int b2p_device_sync(int device)
 {
   CK(NULL, cudaSetDevice(device));
   CK(NULL, cudaDeviceSynchronize());
+  return B2P_OK;
+}
+
+/* ----------------------------------------------- link probe and chunk split */
+
+int b2p_probe_h2d(const int *devices, int n, size_t bytes, int reps, double *gbps_out)
+{
+  if (!devices || !gbps_out || n < 1 || n > B2P_MAX_GROUP || bytes == 0)
+    FAIL(NULL, B2P_EINVAL, "b2p_probe_h2d: bad argument");
+  if (reps < 1) reps = 1;
+  void *host = NULL;
+  void *dev[B2P_MAX_GROUP] = {0};
+  cudaStream_t st[B2P_MAX_GROUP] = {0};
+  cudaEvent_t e0[B2P_MAX_GROUP] = {0}, e1[B2P_MAX_GROUP] = {0};
+  cudaError_t e = cudaHostAlloc(&host, bytes, cudaHostAllocPortable);
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    if ((e = cudaSetDevice(devices[i])) != cudaSuccess) break;
+    if ((e = cudaMalloc(&dev[i], bytes)) != cudaSuccess) break;
+    if ((e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking)) != cudaSuccess) break;
+    if ((e = cudaEventCreate(&e0[i])) != cudaSuccess) break;
+    if ((e = cudaEventCreate(&e1[i])) != cudaSuccess) break;
+    e = cudaMemcpyAsync(dev[i], host, bytes, cudaMemcpyHostToDevice, st[i]); /* warm-up */
+  }
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    cudaSetDevice(devices[i]);
+    e = cudaStreamSynchronize(st[i]);
+  }
+  /* all links at once: every device's copies are queued before any is waited for */
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    cudaSetDevice(devices[i]);
+    e = cudaEventRecord(e0[i], st[i]);
+  }
+  for (int r = 0; r < reps && e == cudaSuccess; ++r)
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+      cudaSetDevice(devices[i]);
+      e = cudaMemcpyAsync(dev[i], host, bytes, cudaMemcpyHostToDevice, st[i]);
+    }
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    cudaSetDevice(devices[i]);
+    e = cudaEventRecord(e1[i], st[i]);
+  }
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    cudaSetDevice(devices[i]);
+    float ms = 0.f;
+    if ((e = cudaEventSynchronize(e1[i])) != cudaSuccess) break;
+    if ((e = cudaEventElapsedTime(&ms, e0[i], e1[i])) != cudaSuccess) break;
+    gbps_out[i] = ms > 0.f ? (double)reps * (double)bytes / (ms * 1e-3) / 1e9 : 0.0;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (devices[i] >= 0) cudaSetDevice(devices[i]);
+    if (e0[i]) cudaEventDestroy(e0[i]);
+    if (e1[i]) cudaEventDestroy(e1[i]);
+    if (st[i]) cudaStreamDestroy(st[i]);
+    if (dev[i]) cudaFree(dev[i]);
+  }
+  if (host) cudaFreeHost(host);
+  CK(NULL, e);
+  return B2P_OK;
+}
+
+int b2p_split_chunks(const double *weights, int n, int nchunk, int *counts)
+{
+  if (!counts || n < 1 || nchunk < 0) FAIL(NULL, B2P_EINVAL, "b2p_split_chunks: bad argument");
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double w = weights ? weights[i] : 1.0;
+    if (!(w >= 0.0)) FAIL(NULL, B2P_EINVAL, "b2p_split_chunks: weights must be >= 0");
+    sum += w;
+  }
+  if (sum <= 0.0) FAIL(NULL, B2P_EINVAL, "b2p_split_chunks: all weights are zero");
+  /* largest remainder: floor of the exact share, then the leftover chunks to the largest
+     fractional parts (ties to the lower index) */
+  double frac[B2P_MAX_GROUP];
+  if (n > B2P_MAX_GROUP) FAIL(NULL, B2P_EINVAL, "b2p_split_chunks: too many parts");
+  int given = 0;
+  for (int i = 0; i < n; ++i) {
+    const double share = (weights ? weights[i] : 1.0) / sum * nchunk;
+    counts[i] = (int)share;
+    frac[i] = share - counts[i];
+    given += counts[i];
+  }
+  while (given < nchunk) {
+    int best = 0;
+    for (int i = 1; i < n; ++i)
+      if (frac[i] > frac[best]) best = i;
+    counts[best] += 1;
+    frac[best] = -1.0;
+    given += 1;
+  }
+  return B2P_OK;
+}
+
+/* ------------------------------------------------------- chunk-group shards */
+
+struct b2p_group {
+  int n;                       /* shards with at least one chunk */
+  b2p_ctx *ctx[B2P_MAX_GROUP];
+  int device[B2P_MAX_GROUP], first[B2P_MAX_GROUP], count[B2P_MAX_GROUP];
+  int nbeam, nch, nchan_total;
+  std::vector<float> tmp;
+  char err[512];
+};
+
+static int group_fail(b2p_group *g, int i, int rc)
+{
+  snprintf(g->err, sizeof(g->err), "shard %d (gpu %d, chunks %d..%d): %s", i, g->device[i], g->first[i],
+           g->first[i] + g->count[i] - 1, b2p_last_error(g->ctx[i]));
+  return rc;
+}
+
+int b2p_group_create(b2p_group **out, const b2p_params *base, const int *devices, const int *nchunks,
+                     int ndev)
+{
+  if (!out || !base || !devices || !nchunks || ndev < 1 || ndev > B2P_MAX_GROUP)
+    FAIL(NULL, B2P_EINVAL, "b2p_group_create: bad argument");
+  *out = NULL;
+  int total = 0;
+  for (int i = 0; i < ndev; ++i) {
+    if (nchunks[i] < 0) FAIL(NULL, B2P_EINVAL, "b2p_group_create: negative chunk count");
+    total += nchunks[i];
+  }
+  if (total != base->nchunk)
+    FAIL(NULL, B2P_EINVAL, "b2p_group_create: chunk counts must add up to params.nchunk");
+  b2p_group *g = new (std::nothrow) b2p_group();
+  if (!g) FAIL(NULL, B2P_ENOMEM, "b2p_group_create: out of host memory");
+  g->n = 0;
+  g->err[0] = 0;
+  g->nbeam = base->nbeam;
+  g->nch = base->nch_per_chunk;
+  g->nchan_total = base->nchunk * base->nch_per_chunk;
+  int first = 0;
+  for (int i = 0; i < ndev; ++i) {
+    if (nchunks[i] == 0) continue;
+    b2p_params p = *base;
+    p.device_id = devices[i];
+    p.nchunk = nchunks[i];
+    p.first_chunk = first;
+    p.nchunk_total = base->nchunk;
+    p.nsplit = 0;
+    p.stage_ndf = 0;
+    const int k = g->n;
+    g->device[k] = devices[i];
+    g->first[k] = first;
+    g->count[k] = nchunks[i];
+    int rc = b2p_create(&g->ctx[k], &p);
+    if (rc) { /* g_create_err holds the message */
+      for (int j = 0; j < k; ++j) b2p_destroy(g->ctx[j]);
+      delete g;
+      return rc;
+    }
+    g->n = k + 1;
+    first += nchunks[i];
+  }
+  g->tmp.resize((size_t)g->nbeam * g->nchan_total);
+  *out = g;
+  return B2P_OK;
+}
+
+void b2p_group_destroy(b2p_group *g)
+{
+  if (!g) return;
+  for (int i = 0; i < g->n; ++i) b2p_destroy(g->ctx[i]);
+  delete g;
+}
+
+const char *b2p_group_last_error(const b2p_group *g) { return g ? g->err : g_create_err; }
+int b2p_group_size(const b2p_group *g) { return g ? g->n : 0; }
+b2p_ctx *b2p_group_ctx(const b2p_group *g, int i) { return (g && i >= 0 && i < g->n) ? g->ctx[i] : NULL; }
+int b2p_group_shard(const b2p_group *g, int i, int *device, int *first_chunk, int *nchunk)
+{
+  if (!g || i < 0 || i >= g->n) return B2P_EINVAL;
+  if (device) *device = g->device[i];
+  if (first_chunk) *first_chunk = g->first[i];
+  if (nchunk) *nchunk = g->count[i];
+  return B2P_OK;
+}
+
+/* shard i's [nbeam][count*nch] spectrum -> channels [first*nch, ...) of out[nbeam][nchan_total] */
+static void group_scatter(const b2p_group *g, int i, const float *part, float *out)
+{
+  const int w = g->count[i] * g->nch;
+  for (int b = 0; b < g->nbeam; ++b)
+    memcpy(out + (size_t)b * g->nchan_total + (size_t)g->first[i] * g->nch, part + (size_t)b * w,
+           (size_t)w * sizeof(float));
+}
+
+int b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf)
+{
+  if (!g) return B2P_EINVAL;
+  /* queue every GPU's copies and kernels first, wait afterwards: one host thread, all links busy */
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_accumulate_host_async(g->ctx[i], hptrs, ndf, 0);
+    if (rc) return group_fail(g, i, rc);
+  }
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_wait_input(g->ctx[i]);
+    if (rc) return group_fail(g, i, rc);
+  }
+  return B2P_OK;
+}
+
+int b2p_group_integrate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, float *out_host)
+{
+  if (!g || !out_host) return B2P_EINVAL;
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_accumulate_host_async(g->ctx[i], hptrs, ndf, 1);
+    if (rc) return group_fail(g, i, rc);
+  }
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_wait_output(g->ctx[i], g->tmp.data());
+    if (rc) return group_fail(g, i, rc);
+    group_scatter(g, i, g->tmp.data(), out_host);
+  }
+  return B2P_OK;
+}
+
+int b2p_group_finish(b2p_group *g, float *out_host)
+{
+  if (!g || !out_host) return B2P_EINVAL;
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_accumulate_host_async(g->ctx[i], NULL, 0, 1); /* ndf 0: finish only */
+    if (rc) return group_fail(g, i, rc);
+  }
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_wait_output(g->ctx[i], g->tmp.data());
+    if (rc) return group_fail(g, i, rc);
+    group_scatter(g, i, g->tmp.data(), out_host);
+  }
+  return B2P_OK;
+}
+
+int b2p_group_reset(b2p_group *g)
+{
+  if (!g) return B2P_EINVAL;
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_reset(g->ctx[i]);
+    if (rc) return group_fail(g, i, rc);
+  }
   return B2P_OK;
 }
 

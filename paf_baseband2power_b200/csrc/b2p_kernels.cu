@@ -30,14 +30,21 @@
  * Detect/integrate (exact mode): IMAD squares, a pair of squares fits uint32
  * (<= 2^31), words are accumulated in uint64 — a channel total is <= 2^52, so
  * the sum is exact and independent of order; CTA partials go to global memory
- * and a second tiny kernel (one warp per channel) adds them and either updates
- * the running accumulator or emits the float32 spectrum.  No atomics anywhere.
+ * and the LAST CTA to finish a (beam, chunk) column — found with one arrival
+ * counter per column — adds the column's partial sums in fixed split order and
+ * either folds them into the running accumulator or emits the float32 spectrum:
+ * one launch per integration.  Sums never go through atomics.
  *
  * Launch chaining: every kernel is launched with programmatic stream
  * serialization (PDL).  A fused kernel releases its dependents at once and only
  * waits for its predecessor (griddepcontrol.wait) right before it writes its
  * partial sums, so on the context's own stream the head of integration N+1
  * overlaps the tail of integration N and the launch gaps disappear.
+ *
+ * Channel-group shards: `nchunk` is the number of chunks this launch covers and
+ * `fpitch` the byte distance between successive data frames of the source, so a
+ * launch can read chunks [c0, c0+nchunk) straight out of full 48-chunk frames
+ * (pitch 344 064 B) or out of a compact staging copy (pitch nchunk*7168).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -204,6 +211,81 @@ __device__ __forceinline__ void cta_reduce_n(const T (&a)[NA], const int (&c)[NA
   }
 }
 
+/* ------------------------------------------- column epilogue (cross-CTA reduce) */
+
+__device__ __forceinline__ float to_f32_rn(unsigned long long v) { return __ull2float_rn(v); }
+__device__ __forceinline__ float to_f32_rn(double v) { return __double2float_rn(v); }
+
+/* barrier over the threads that take part in an epilogue: the whole CTA (ID 0) or the
+   consumer threads of the TMA kernel (named barrier ID, COUNT threads) */
+template <int ID, int COUNT> __device__ __forceinline__ void epi_bar()
+{
+  if (ID == 0)
+    __syncthreads();
+  else
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
+/*
+ * Arrival: every CTA that has stored the partial sums of one (beam, column) item calls
+ * this with all `nt` participating threads; the partial stores must precede it in program
+ * order in the threads that made them.  Returns true (to all threads) in the one CTA that
+ * arrived last — the partial sums of all nsplit splits of the column are then visible.
+ */
+template <int ID, int COUNT>
+__device__ __forceinline__ bool column_arrive(unsigned int *cnt, uint32_t nsplit, uint32_t *flag,
+                                              int tid)
+{
+  __threadfence(); /* release: this thread's partial sums before the arrival */
+  epi_bar<ID, COUNT>();
+  if (tid == 0) *flag = (atomicAdd(cnt, 1u) == nsplit - 1u) ? 1u : 0u;
+  epi_bar<ID, COUNT>();
+  const bool last = *flag != 0u;
+  if (last) __threadfence(); /* acquire side */
+  return last;
+}
+
+/*
+ * Fold of one column by its last CTA: `ncol` channels starting at channel col0.  Thread t <
+ * LP*ncol takes channel t % ncol and sums splits l, l+LP, ... (l = t / ncol) in ascending
+ * order; ncol threads then add the LP lane sums in ascending order and the running
+ * accumulator — a fixed order whoever arrives last.  finish: emit (float)total*scale (one RN
+ * conversion, one fp32 multiply) and clear the accumulator; otherwise store the total back.
+ * Partial sums were written by other SMs: read them at L2 (ld.global.cg).
+ */
+template <typename T, int ID, int COUNT>
+__device__ __forceinline__ void column_fold(const T *__restrict__ partials, T *fold, const B2pFold &F,
+                                            uint32_t lbeam, int row, uint32_t nsplit, size_t nchan,
+                                            uint32_t col0, int ncol, int tid, int nt,
+                                            unsigned int *cnt)
+{
+  int LP = nt / ncol;
+  if (LP > 32) LP = 32;
+  if (tid < LP * ncol) {
+    const int ch = tid % ncol, l = tid / ncol;
+    const T *p = partials + (size_t)lbeam * nsplit * nchan + col0 + ch;
+    T v = 0;
+    for (uint32_t sp = l; sp < nsplit; sp += LP) v += __ldcg(p + (size_t)sp * nchan);
+    fold[tid] = v;
+  }
+  epi_bar<ID, COUNT>();
+  if (tid < ncol) {
+    T tot = 0;
+    for (int l = 0; l < LP; ++l) tot += fold[l * ncol + tid];
+    const size_t idx = (size_t)row * nchan + col0 + tid;
+    T *acc = (T *)F.acc;
+    tot += acc[idx];
+    if (F.finish) {
+      F.out[idx] = __fmul_rn(to_f32_rn(tot), F.scale);
+      acc[idx] = 0;
+    } else {
+      acc[idx] = tot;
+    }
+  }
+  if (tid == 0) *cnt = 0u; /* clean for the next launch (and for a CUDA-graph replay) */
+  epi_bar<ID, COUNT>();    /* `fold` may be reused by the caller */
+}
+
 /* ------------------------------------- LDG.256 kernel, BMF geometry (default) */
 /*
  * 224 threads cover a 7168-byte packet with 32 bytes each = payload words
@@ -215,21 +297,23 @@ __device__ __forceinline__ void cta_reduce_n(const T (&a)[NA], const int (&c)[NA
  */
 template <typename Acc, bool BE, int UF, int MINB>
 __global__ void __launch_bounds__(224, MINB)
-b2p_fused_ldg256_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t ndf,
-                     const int early, typename Acc::type *__restrict__ partials)
+b2p_fused_ldg256_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t fpitch,
+                     const uint64_t ndf, const int early, typename Acc::type *__restrict__ partials,
+                     const B2pFold fold)
 {
   typedef typename Acc::type T;
   constexpr int THREADS = 224;
-  __shared__ T red[(THREADS / 32) * kNchBmf];
+  __shared__ T red[THREADS]; /* [7 warps][7 ch] for the CTA sum, [32 lanes][7 ch] for the fold */
+  __shared__ uint32_t last_flag;
   pdl_release_dependents();
   if (!early) pdl_wait_predecessor();
   const int j = threadIdx.x;
   const uint32_t chunk = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y, beam = blockIdx.z;
   uint64_t f0, f1;
   split_range(ndf, split, nsplit, f0, f1);
-  const size_t fstride = (size_t)nchunk * kPktBytes; /* bytes per data frame */
+  const size_t fstride = (size_t)fpitch; /* bytes per data frame of the source */
   const unsigned char *p =
-      (const unsigned char *)beams.ptr[beam] + (f0 * nchunk + chunk) * kPktBytes + j * 32;
+      (const unsigned char *)beams.ptr[beam] + f0 * fstride + (size_t)chunk * kPktBytes + j * 32;
   T a[4] = {0, 0, 0, 0};
   uint64_t f = f0;
   for (; f + UF <= f1; f += UF) {
@@ -252,8 +336,13 @@ b2p_fused_ldg256_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t
   T *dst = partials + ((size_t)beam * nsplit + split) * nchan + (size_t)chunk * kNchBmf;
   const int c[4] = {(4 * j) % kNchBmf, (4 * j + 1) % kNchBmf, (4 * j + 2) % kNchBmf,
                     (4 * j + 3) % kNchBmf};
-  if (early) pdl_wait_predecessor(); /* the previous reduce kernel has consumed `partials` */
+  /* the previous kernel of the stream has finished with `partials`, the counters and acc */
+  if (early) pdl_wait_predecessor();
   cta_reduce_n<T, 4>(a, c, kNchBmf, red, dst, j, THREADS);
+  unsigned int *cnt = fold.colcnt + beam * nchunk + chunk;
+  if (!column_arrive<0, 0>(cnt, nsplit, &last_flag, j)) return;
+  column_fold<T, 0, 0>(partials, red, fold, beam, beams.slot[beam], nsplit, nchan, chunk * kNchBmf,
+                       kNchBmf, j, THREADS, cnt);
 }
 
 /* ------------------------------------------------ LDG.128 kernel, any geometry */
@@ -265,20 +354,23 @@ b2p_fused_ldg256_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t
  */
 template <typename Acc, bool BE, int UF, bool CALIB>
 __global__ void b2p_fused_ldg128(const B2pBeams beams, const uint32_t nchunk, const uint32_t nch,
-                                 const uint32_t units_per_pkt, const uint64_t ndf, const int early,
-                                 typename Acc::type *__restrict__ partials)
+                                 const uint32_t units_per_pkt, const uint64_t fpitch,
+                                 const uint64_t ndf, const int early,
+                                 typename Acc::type *__restrict__ partials, const B2pFold fold)
 {
   typedef typename Acc::type T;
   extern __shared__ __align__(16) unsigned char smem_any[];
-  T *red = (T *)smem_any;
+  T *red = (T *)smem_any; /* max([nwarps][nch], [32][nch]) elements */
+  __shared__ uint32_t last_flag;
   pdl_release_dependents();
   if (!early) pdl_wait_predecessor();
   const int j = threadIdx.x, nt = blockDim.x;
   const uint32_t chunk = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y, beam = blockIdx.z;
   uint64_t f0, f1;
   split_range(ndf, split, nsplit, f0, f1);
-  const size_t fstride = (size_t)nchunk * units_per_pkt;
-  const uint4 *base = (const uint4 *)beams.ptr[beam] + (f0 * nchunk + chunk) * units_per_pkt;
+  const size_t fstride = (size_t)(fpitch / 16u); /* uint4 units per data frame of the source */
+  const uint4 *base =
+      (const uint4 *)beams.ptr[beam] + f0 * fstride + (size_t)chunk * units_per_pkt;
   T a0 = 0, a1 = 0;
   for (uint32_t u = j; u < units_per_pkt; u += nt) {
     const uint4 *p = base + u;
@@ -312,6 +404,10 @@ __global__ void b2p_fused_ldg128(const B2pBeams beams, const uint32_t nchunk, co
   const int c[2] = {(int)((2 * j) % nch), (int)((2 * j + 1) % nch)};
   if (early) pdl_wait_predecessor();
   cta_reduce_n<T, 2>(a, c, (int)nch, red, dst, j, nt);
+  unsigned int *cnt = fold.colcnt + beam * nchunk + chunk;
+  if (!column_arrive<0, 0>(cnt, nsplit, &last_flag, j)) return;
+  column_fold<T, 0, 0>(partials, red, fold, beam, beams.slot[beam], nsplit, nchan, chunk * nch,
+                       (int)nch, j, nt, cnt);
 }
 
 /* Bandwidth calibration only (B2P_CALIB=1): flat grid-stride read of the block,
@@ -414,7 +510,12 @@ template <int G, int NSTAGE> struct TmaSmem {
   static constexpr int kBarOff = NSTAGE * kStageBytes;
   static constexpr int kTagOff = kBarOff + 2 * NSTAGE * 8;
   static constexpr int kRedOff = kTagOff + NSTAGE * 8;
-  static constexpr int kBytes = kRedOff + kTmaConsumerWarps * G * kNchBmf * 8;
+  /* [14 warps][G*7] for the item sum; the column fold needs [lanes][G*7] <= 448 elements */
+  static constexpr int kRedElems = kTmaConsumerWarps * G * kNchBmf > kTmaConsumers
+                                       ? kTmaConsumerWarps * G * kNchBmf
+                                       : kTmaConsumers;
+  static constexpr int kFlagOff = kRedOff + kRedElems * 8;
+  static constexpr int kBytes = kFlagOff + 16;
 };
 
 constexpr uint32_t kTagLast = 0x80000000u; /* last frame of the item */
@@ -422,9 +523,10 @@ constexpr uint32_t kTagEnd = 0xFFFFFFFFu;  /* no more work for this CTA */
 
 template <typename Acc, bool BE, int G, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(kTmaThreads, MINB)
-b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t ndf,
-                  const uint32_t nsplit, const uint32_t nitems, const int early,
-                  unsigned int *__restrict__ ticket, typename Acc::type *__restrict__ partials)
+b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t fpitch,
+                  const uint64_t ndf, const uint32_t nsplit, const uint32_t nitems, const int early,
+                  unsigned int *__restrict__ ticket, typename Acc::type *__restrict__ partials,
+                  const B2pFold fold)
 {
   typedef typename Acc::type T;
   typedef TmaSmem<G, NSTAGE> S;
@@ -433,6 +535,7 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
   uint64_t *empty = full + NSTAGE;
   volatile uint32_t *tag = (volatile uint32_t *)(smem + S::kTagOff);
   T *red = (T *)(smem + S::kRedOff);
+  uint32_t *last_flag = (uint32_t *)(smem + S::kFlagOff);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ngroups = nchunk / G;
@@ -454,13 +557,16 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
       for (;;) {
         const uint32_t item = atomicAdd(ticket, 1u);
         const bool end = item >= nitems;
+        /* every CTA draws exactly one ticket past the end: the last such draw of the launch
+           leaves the counter at zero again for the launch that reuses it (or a graph replay) */
+        if (item == nitems + gridDim.x - 1u) atomicExch(ticket, 0u);
         uint64_t f0 = 0, f1 = 1;
         const unsigned char *src = nullptr;
         if (!end) {
           const uint32_t group = item % ngroups, rest = item / ngroups;
           const uint32_t split = rest % nsplit, beam = rest / nsplit;
           split_range(ndf, split, nsplit, f0, f1);
-          src = (const unsigned char *)beams.ptr[beam] + (f0 * nchunk + (uint64_t)group * G) * kPktBytes;
+          src = (const unsigned char *)beams.ptr[beam] + f0 * fpitch + (uint64_t)group * G * kPktBytes;
           if (f1 == f0) { /* an empty split still owes its (zero) partial sums */
             const uint32_t s = it % NSTAGE, k = it / NSTAGE;
             if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
@@ -470,7 +576,7 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
             continue;
           }
         }
-        const size_t fstride = (size_t)nchunk * kPktBytes;
+        const size_t fstride = (size_t)fpitch;
         for (uint64_t f = f0; f < f1; ++f, ++it, src += fstride) {
           const uint32_t s = it % NSTAGE, k = it / NSTAGE;
           if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
@@ -532,65 +638,40 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t nd
         if (lane == 0) red[warp * (G * kNchBmf) + g * kNchBmf + ch] = v;
       }
     consumer_bar();
+    /* the previous kernel of the stream has finished with `partials`, the counters and acc */
+    if (!waited) pdl_wait_predecessor();
+    waited = true;
     if (tid < G * kNchBmf) {
-      if (!waited) pdl_wait_predecessor();
       T sum = 0;
       for (int w = 0; w < kTmaConsumerWarps; ++w) sum += red[w * (G * kNchBmf) + tid];
       dst[tid] = sum;
     }
-    waited = true;
-    consumer_bar(); /* red is reused by the next item */
+    /* column (beam, chunk group) complete?  its last item folds all nsplit partial sums */
+    unsigned int *cnt = fold.colcnt + beam * ngroups + group;
+    if (column_arrive<1, kTmaConsumers>(cnt, nsplit, last_flag, tid))
+      column_fold<T, 1, kTmaConsumers>(partials, red, fold, beam, beams.slot[beam], nsplit, nchan,
+                                       group * G * kNchBmf, G * kNchBmf, tid, kTmaConsumers, cnt);
 #pragma unroll
     for (int g = 0; g < G; ++g) a[g][0] = a[g][1] = 0;
   }
 }
 
-/* -------------------------------------------- cross-CTA reduce and finish */
-
-__device__ __forceinline__ float to_f32_rn(unsigned long long v) { return __ull2float_rn(v); }
-__device__ __forceinline__ float to_f32_rn(double v) { return __double2float_rn(v); }
-
+/* ------------------------------------------------------- stand-alone finish */
 /*
- * One warp per (accumulator row, channel): lanes stride over the time splits of
- * the row's pending partial sums (if any), a fixed xor tree joins them, lane 0
- * adds the running accumulator.  FINISH: emit (float)total*scale (one RN
- * conversion, one fp32 multiply) and clear the accumulator; otherwise store the
- * total back.  Replaces any atomic cross-block reduction.
+ * Used only when an integration is closed without a fused launch to ride on (b2p_finish
+ * after plain accumulate calls): out = (float)acc * scale, acc = 0.  The steady-state path
+ * (b2p_integrate_*) finishes inside the fused kernel and never launches this.
  */
-template <typename T, bool FINISH>
+template <typename T>
 __global__ void __launch_bounds__(256)
-b2p_reduce_k(const B2pSlots slots, const uint32_t nrows, const uint32_t nsplit,
-             const uint32_t nchan, const T *__restrict__ partials, T *__restrict__ acc,
-             float *__restrict__ out, const float scale, unsigned int *__restrict__ ticket)
+b2p_finish_k(const uint32_t n, T *__restrict__ acc, float *__restrict__ out, const float scale)
 {
   pdl_release_dependents();
   pdl_wait_predecessor();
-  /* the fused launch this kernel follows is complete: its work-item counter goes back to
-     zero, so the same counter is clean when the slot comes round again or when a captured
-     CUDA graph containing the pair is replayed */
-  if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= nrows * nchan) return;
-  const uint32_t row = w / nchan, k = w % nchan;
-  const int lb = slots.lb[row];
-  T s = 0;
-  if (lb >= 0) {
-    const T *p = partials + (size_t)lb * nsplit * nchan + k;
-    for (uint32_t i = lane; i < nsplit; i += 32) s += p[(size_t)i * nchan];
-    s = warp_sum(s);
-  } else if (!FINISH) {
-    return;
-  }
-  if (lane == 0) {
-    const size_t idx = (size_t)row * nchan + k;
-    const T total = acc[idx] + s;
-    if (FINISH) {
-      out[idx] = __fmul_rn(to_f32_rn(total), scale);
-      acc[idx] = 0;
-    } else {
-      acc[idx] = total;
-    }
-  }
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = __fmul_rn(to_f32_rn(acc[i]), scale);
+  acc[i] = 0;
 }
 
 /* ------------------------------------------------------- synthetic stream */
@@ -663,8 +744,8 @@ cudaError_t launch_tma(const B2pLaunch &L, cudaStream_t st)
   uint32_t grid = (uint32_t)L.sm_count * MINB;
   if (grid > nitems) grid = nitems;
   return launch_k(b2p_fused_tma_bmf<Acc, BE, G, NSTAGE, MINB>, dim3(grid), dim3(kTmaThreads), S::kBytes,
-                  st, L.pdl != 0, L.beams, (uint32_t)L.nchunk, L.ndf, (uint32_t)L.nsplit, nitems,
-                  L.early, L.ticket, (typename Acc::type *)L.partials);
+                  st, L.pdl != 0, L.beams, (uint32_t)L.nchunk, L.fpitch, L.ndf, (uint32_t)L.nsplit,
+                  nitems, L.early, L.ticket, (typename Acc::type *)L.partials, L.fold);
 }
 
 template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, cudaStream_t st)
@@ -684,31 +765,34 @@ template <typename Acc, bool BE> cudaError_t launch_fused_t(const B2pLaunch &L, 
   }
   const dim3 grid((unsigned)L.nchunk, (unsigned)L.nsplit, (unsigned)L.nbeam);
   T *part = (T *)L.partials;
+  const size_t sh448 = 32 * 7 * sizeof(T); /* >= [14 warps][7] and = [32 lanes][7] */
   if (bmf && L.calib && L.variant == 9) /* calibration only: flat streaming read */
     return launch_k(b2p_calib_flat<T>, dim3(4 * L.sm_count, L.nbeam), dim3(256), 0, st, false,
                     L.beams, L.ndf * (uint64_t)L.nchunk * kUnitsBmf, part);
   if (bmf && L.calib && L.variant == 7) /* calibration only: same pattern, loads + XOR */
-    return launch_k(b2p_fused_ldg128<Acc, BE, 8, true>, grid, dim3(448), 14 * 7 * sizeof(T), st,
-                    pdl, L.beams, (uint32_t)L.nchunk, 7u, (uint32_t)kUnitsBmf, L.ndf, L.early, part);
+    return launch_k(b2p_fused_ldg128<Acc, BE, 8, true>, grid, dim3(448), sh448, st, pdl, L.beams,
+                    (uint32_t)L.nchunk, 7u, (uint32_t)kUnitsBmf, L.fpitch, L.ndf, L.early, part,
+                    L.fold);
   if (bmf && L.variant == 1) /* tuning point: 128-bit loads, 448 threads, 8 frames in flight */
-    return launch_k(b2p_fused_ldg128<Acc, BE, 8, false>, grid, dim3(448), 14 * 7 * sizeof(T), st,
-                    pdl, L.beams, (uint32_t)L.nchunk, 7u, (uint32_t)kUnitsBmf, L.ndf, L.early, part);
+    return launch_k(b2p_fused_ldg128<Acc, BE, 8, false>, grid, dim3(448), sh448, st, pdl, L.beams,
+                    (uint32_t)L.nchunk, 7u, (uint32_t)kUnitsBmf, L.fpitch, L.ndf, L.early, part,
+                    L.fold);
   if (bmf) {
     if (L.variant == 2)
       return launch_k(b2p_fused_ldg256_bmf<Acc, BE, 2, 6>, grid, dim3(224), 0, st, pdl, L.beams,
-                      (uint32_t)L.nchunk, L.ndf, L.early, part);
+                      (uint32_t)L.nchunk, L.fpitch, L.ndf, L.early, part, L.fold);
     if (L.variant == 3)
       return launch_k(b2p_fused_ldg256_bmf<Acc, BE, 8, 2>, grid, dim3(224), 0, st, pdl, L.beams,
-                      (uint32_t)L.nchunk, L.ndf, L.early, part);
+                      (uint32_t)L.nchunk, L.fpitch, L.ndf, L.early, part, L.fold);
     /* default: 4 x 256-bit loads in flight per thread, 4 CTAs/SM — fastest measured */
     return launch_k(b2p_fused_ldg256_bmf<Acc, BE, 4, 4>, grid, dim3(224), 0, st, pdl, L.beams,
-                    (uint32_t)L.nchunk, L.ndf, L.early, part);
+                    (uint32_t)L.nchunk, L.fpitch, L.ndf, L.early, part, L.fold);
   }
   const int nt = 32 * L.nch;
-  const size_t sh = (size_t)(nt / 32) * L.nch * sizeof(T);
+  const size_t sh = (size_t)32 * L.nch * sizeof(T); /* nwarps == nch <= 32 */
   return launch_k(b2p_fused_ldg128<Acc, BE, 4, false>, grid, dim3(nt), sh, st, pdl, L.beams,
-                  (uint32_t)L.nchunk, (uint32_t)L.nch, (uint32_t)(L.nsamp * L.nch / 2), L.ndf,
-                  L.early, part);
+                  (uint32_t)L.nchunk, (uint32_t)L.nch, (uint32_t)(L.nsamp * L.nch / 2), L.fpitch,
+                  L.ndf, L.early, part, L.fold);
 }
 
 template <typename Acc, bool BE, int G, int NSTAGE, int MINB = 1> cudaError_t configure_tma()
@@ -726,17 +810,11 @@ template <typename Acc, bool BE> cudaError_t configure_all()
   return configure_tma<Acc, BE, 1, kTmaStagesG1>();
 }
 
-template <typename T> cudaError_t launch_reduce_t(const B2pReduce &R, cudaStream_t st)
+template <typename T> cudaError_t launch_finish_t(const B2pFinish &R, cudaStream_t st)
 {
-  const uint32_t nwarps = (uint32_t)R.nrows * (uint32_t)R.nchan;
-  const dim3 grid((nwarps * 32 + 255) / 256);
-  if (R.finish)
-    return launch_k(b2p_reduce_k<T, true>, grid, dim3(256), 0, st, R.pdl != 0, R.slots,
-                    (uint32_t)R.nrows, (uint32_t)R.nsplit, (uint32_t)R.nchan,
-                    (const T *)R.partials, (T *)R.acc, R.out, R.scale, R.ticket);
-  return launch_k(b2p_reduce_k<T, false>, grid, dim3(256), 0, st, R.pdl != 0, R.slots,
-                  (uint32_t)R.nrows, (uint32_t)R.nsplit, (uint32_t)R.nchan, (const T *)R.partials,
-                  (T *)R.acc, R.out, R.scale, R.ticket);
+  const uint32_t n = (uint32_t)R.nrows * (uint32_t)R.nchan;
+  return launch_k(b2p_finish_k<T>, dim3((n + 255) / 256), dim3(256), 0, st, R.pdl != 0, n,
+                  (T *)R.acc, R.out, R.scale);
 }
 } /* namespace */
 
@@ -757,10 +835,10 @@ cudaError_t b2p_launch_fused(const B2pLaunch &L, cudaStream_t st)
   return L.big_endian ? launch_fused_t<AccExact, true>(L, st) : launch_fused_t<AccExact, false>(L, st);
 }
 
-cudaError_t b2p_launch_reduce(const B2pReduce &R, cudaStream_t st)
+cudaError_t b2p_launch_finish(const B2pFinish &R, cudaStream_t st)
 {
-  if (R.mode == B2P_MODE_FLOAT) return launch_reduce_t<double>(R, st);
-  return launch_reduce_t<unsigned long long>(R, st);
+  if (R.mode == B2P_MODE_FLOAT) return launch_finish_t<double>(R, st);
+  return launch_finish_t<unsigned long long>(R, st);
 }
 
 cudaError_t b2p_launch_synth(void *dptr, uint64_t ndf, int nchunk, int nch, int nsamp,

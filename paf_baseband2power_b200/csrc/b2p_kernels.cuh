@@ -18,16 +18,22 @@ struct B2pBeams {
   int slot[B2P_MAX_BEAMS];
 };
 
-/* For the cross-CTA reduce: lb[row] = index of accumulator row `row` among the beams
-   of the pending fused launch, or -1 when the row has no pending partial sums. */
-struct B2pSlots {
-  int lb[B2P_MAX_BEAMS];
+/* Epilogue of a fused launch: the last CTA of each (beam, column) adds the column's
+   partial sums to accumulator row slot[beam] and stores the total back (finish = 0) or
+   emits (float)total*scale to `out` and clears the accumulator (finish = 1). */
+struct B2pFold {
+  void *acc;            /* [ctx nbeam][nchan] uint64 (exact) or double (float mode) */
+  float *out;           /* [ctx nbeam][nchan] float32, written when finish */
+  unsigned int *colcnt; /* [launch nbeam][columns] arrival counters, all zero between launches */
+  float scale;
+  int finish;
 };
 
 struct B2pLaunch {
   B2pBeams beams;
   int nbeam;       /* beams in this launch */
-  int nchunk, nch, nsamp;
+  int nchunk, nch, nsamp; /* nchunk: chunks covered by this launch (a shard's local count) */
+  uint64_t fpitch;        /* bytes between successive data frames of the source */
   int big_endian;
   int mode;        /* B2P_MODE_* */
   int kernel;      /* B2P_KERNEL_LDG / B2P_KERNEL_TMA (resolved, not AUTO) */
@@ -38,9 +44,10 @@ struct B2pLaunch {
   int pdl;         /* launch with programmatic stream serialization */
   int early;       /* input independent of the stream's previous kernel: start before it ends */
   uint64_t ndf;    /* frames per beam in this launch */
-  unsigned int *ticket; /* zeroed work-item counter of this launch (TMA kernel) */
+  unsigned int *ticket; /* zeroed work-item counter of this launch (TMA kernel); the kernel
+                           puts it back to zero itself */
   void *partials;  /* [nbeam][nsplit][nchan] uint64 (exact) or double (float mode) */
-  void *acc;       /* [ctx nbeam][nchan]     uint64 (exact) or double (float mode) */
+  B2pFold fold;
 };
 
 /* true when (nch, nsamp) is the BMF geometry the specialised kernels cover */
@@ -50,22 +57,15 @@ static inline bool b2p_is_bmf_geometry(int nch, int nsamp) { return nch == 7 && 
 int b2p_tma_group(int nchunk);
 
 cudaError_t b2p_launch_fused(const B2pLaunch &L, cudaStream_t st);
-struct B2pReduce {
-  B2pSlots slots;
-  int nrows;       /* accumulator rows of the context (its nbeam) */
-  int nsplit;      /* splits of the pending launch */
-  int nchan;
-  int mode;
-  int finish;      /* 1: emit float32 spectrum and clear; 0: fold partials into acc */
-  int pdl;
-  const void *partials;
+/* Stand-alone finish (no fused launch to ride on): out = (float)acc*scale, acc = 0. */
+struct B2pFinish {
+  int nrows, nchan, mode, pdl;
   void *acc;
   float *out;
   float scale;
-  unsigned int *ticket; /* counter of the pending fused launch, reset here (NULL: none) */
 };
 
-cudaError_t b2p_launch_reduce(const B2pReduce &R, cudaStream_t st);
+cudaError_t b2p_launch_finish(const B2pFinish &R, cudaStream_t st);
 cudaError_t b2p_launch_synth(void *dptr, uint64_t ndf, int nchunk, int nch, int nsamp,
                              int big_endian, uint64_t seed, uint64_t first_word, int mode,
                              cudaStream_t st);

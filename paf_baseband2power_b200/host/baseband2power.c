@@ -192,27 +192,31 @@ int do_baseband2power(conf_t *conf)
       uint64_t n = conf->ndf_integration - in_integration;
       if (n > ndf - done) n = ndf - done;
       const void *ptr = blk + done * frame_bytes;
-      if (b2p_accumulate_host(conf->ctx, &ptr, n) != B2P_OK) {
-        STAGE_ERR(conf, "b2p_accumulate_host failed: %s\n", b2p_last_error(conf->ctx));
-        return EXIT_FAILURE;
-      }
-      done += n;
-      in_integration += n;
-      if (in_integration == conf->ndf_integration) {
+      const int closes = in_integration + n == conf->ndf_integration;
+      if (!closes) {
+        if (b2p_accumulate_host(conf->ctx, &ptr, n) != B2P_OK) {
+          STAGE_ERR(conf, "b2p_accumulate_host failed: %s\n", b2p_last_error(conf->ctx));
+          return EXIT_FAILURE;
+        }
+      } else {
+        /* these frames complete an integration: the kernel of the last staging piece emits
+           the spectrum itself (one launch per piece, no separate finish), straight into
+           the output ring block */
         uint64_t out_id = 0;
         char *out = ipcio_open_block_write(conf->hdu_out->data_block, &out_id);
         if (!out) {
           STAGE_ERR(conf, "Can not open an output block\n");
           return EXIT_FAILURE;
         }
-        if (b2p_finish(conf->ctx, (float *)out) != B2P_OK) {
-          STAGE_ERR(conf, "b2p_finish failed: %s\n", b2p_last_error(conf->ctx));
+        if (b2p_integrate_host(conf->ctx, &ptr, n, (float *)out) != B2P_OK) {
+          STAGE_ERR(conf, "b2p_integrate_host failed: %s\n", b2p_last_error(conf->ctx));
           return EXIT_FAILURE;
         }
         ipcio_close_block_write(conf->hdu_out->data_block, conf->rbufsz_out);
         conf->nblocks_out++;
-        in_integration = 0;
       }
+      done += n;
+      in_integration = closes ? 0 : in_integration + n;
     }
     ipcio_close_block_read(conf->hdu_in->data_block, bytes);
     conf->nblocks_in++;

@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in _declared_functions():
         assert hasattr(lib, name), f"{name} declared in b2p.h but not exported"
-    assert _lib.load().b2p_version() == b"0.1.0"
+    hdr = open(os.path.join(ROOT, "include", "b2p.h")).read()
+    assert _lib.load().b2p_version() == re.search(r'#define B2P_VERSION "([^"]+)"', hdr).group(1).encode()
 
 
 def test_params_struct_matches_header_defaults():
@@ -43,6 +44,18 @@ def test_params_struct_matches_header_defaults():
     assert (p.nchunk, p.nch_per_chunk, p.nsamp_df, p.big_endian) == (48, 7, 128, 1)
     assert (p.scale, p.mode, p.nbeam, p.kernel, p.nsplit) == (1.0, 0, 1, 0, 0)
     assert (p.stage_ndf, p.nstage_bufs, p.device_id) == (0, 0, 0)
+    assert (p.first_chunk, p.nchunk_total) == (0, 0)
+    # the ctypes mirror and the C struct must agree on the size (a drifted field would shift all)
+    assert ctypes.sizeof(_lib.B2pParams) == 64
+
+
+def test_no_batched_memcpy_names_in_the_artefact():
+    """the shipped library is linked against the shared CUDA runtime, so it carries
+    no runtime symbol names beyond the calls this project makes."""
+    from paf_baseband2power_b200 import _lib
+    blob = open(_lib.LIB_PATH, "rb").read()
+    for name in (b"MemcpyBatchAsync", b"Memcpy3DBatchAsync"):
+        assert name not in blob
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -367,3 +367,305 @@ def test_cuda_graph_capture_and_replay(b2p, oracle_mod, kernel):
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want[i].view(np.uint32)), (kernel, rep)
     st.close()
+
+
+# ------------------------------------------------------------------ round 2
+# one launch per integration, channel-group shards, asynchronous host path
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_integrate_device_is_one_launch(b2p, oracle_mod, kernel):
+    """b2p_integrate_device: accumulate + cross-CTA reduce + finish inside a single kernel."""
+    g = oracle_mod.Geometry()
+    ndf = 300
+    block = oracle_mod.synth_fill(ndf, seed=901, mode=1)
+    want_s = oracle_mod.accumulate_omp(block)
+    st = b2p.Baseband2Power(kernel=kernel)
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    out = b2p.DeviceBuffer(g.nchan * 4)
+    n0 = st.launch_count
+    st.integrate_device([dev], ndf, out)
+    assert st.launch_count == n0 + 1
+    b2p.device_sync(0)
+    got = out.download().view(np.float32)
+    assert np.array_equal(got.view(np.uint32), oracle_mod.finish(want_s).view(np.uint32))
+    assert not st.read_sums().any()                   # the integration was closed and cleared
+    # earlier accumulate calls are folded into the integration the launch closes
+    st.accumulate_device([dev], 100)
+    st.accumulate_device([dev.ptr + 100 * g.frame_bytes], 50)
+    st.integrate_device([dev.ptr + 150 * g.frame_bytes], 150, out)
+    b2p.device_sync(0)
+    got = out.download().view(np.float32)
+    assert np.array_equal(got.view(np.uint32), oracle_mod.finish(want_s).view(np.uint32))
+    dev.free()
+    out.free()
+    st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_chained_single_launch_integrations(b2p, oracle_mod, kernel):
+    """60 integrations back to back, one PDL-chained launch each, results kept on the device."""
+    g = oracle_mod.Geometry()
+    nblk, ndf, nrun = 4, 260, 60
+    blocks = [oracle_mod.synth_fill(ndf, seed=930 + i, mode=i % 2) for i in range(nblk)]
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(b)) for b in blocks]
+    dev = [b2p.DeviceBuffer(b.nbytes) for b in blocks]
+    for d, b in zip(dev, blocks):
+        d.upload(b)
+    outs = b2p.DeviceBuffer(nrun * g.nchan * 4)
+    st = b2p.Baseband2Power(kernel=kernel)
+    n0 = st.launch_count
+    for i in range(nrun):
+        st.integrate_device([dev[i % nblk]], ndf, outs.ptr + i * g.nchan * 4)
+    assert st.launch_count == n0 + nrun
+    b2p.device_sync(0)
+    got = outs.download().view(np.float32).reshape(nrun, g.nchan)
+    for i in range(nrun):
+        assert np.array_equal(got[i].view(np.uint32), want[i % nblk].view(np.uint32)), i
+    st.close()
+    for d in dev:
+        d.free()
+    outs.free()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_multibeam_integrate_with_float_and_scale(b2p, oracle_mod, kernel):
+    nbeam, ndf = 3, 40
+    g = oracle_mod.Geometry()
+    blocks = [oracle_mod.synth_fill(ndf, seed=940 + b, mode=1) for b in range(nbeam)]
+    dev = b2p.DeviceBuffer(nbeam * blocks[0].nbytes)
+    dev.upload(np.concatenate(blocks))
+    out = b2p.DeviceBuffer(nbeam * g.nchan * 4)
+    for mode in ("exact", "float"):
+        st = b2p.Baseband2Power(kernel=kernel, nbeam=nbeam, mode=mode, scale=2.0 ** -12)
+        st.integrate_device([dev.ptr + b * blocks[0].nbytes for b in range(nbeam)], ndf, out)
+        b2p.device_sync(0)
+        got = out.download().view(np.float32).reshape(nbeam, g.nchan)
+        for b in range(nbeam):
+            s = oracle_mod.accumulate(blocks[b])
+            if mode == "exact":
+                assert np.array_equal(got[b].view(np.uint32), oracle_mod.finish(s, 2.0 ** -12).view(np.uint32))
+            else:
+                ref = s.astype(np.float64) * 2.0 ** -12
+                assert (np.abs(got[b] - ref) / ref).max() <= 1e-6
+        st.close()
+    dev.free()
+    out.free()
+
+
+def _shard_ranges(counts):
+    first = 0
+    for n in counts:
+        if n:
+            yield first, n
+        first += n
+
+
+SPLITS = [[6] * 8, [5, 5, 5, 5, 7, 7, 7, 7], [48], [1, 47], [13, 0, 35], [3, 9, 11, 25]]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("counts", SPLITS)
+def test_chunk_group_shards_concatenate_bit_exact(b2p, oracle_mod, kernel, counts):
+    """Every shard reads its chunk columns out of the full-frame block (device-strided, staged
+    2-D H2D, and zero-copy mapped); the channel ranges put side by side equal the oracle's
+    spectrum of the whole block."""
+    g = oracle_mod.Geometry()
+    ndf = 70
+    block = oracle_mod.synth_fill(ndf, seed=950, mode=1)
+    want = oracle_mod.accumulate_omp(block)
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    pin = b2p.PinnedBuffer(block.nbytes)
+    pin.array[:] = block
+    got_dev = np.zeros(g.nchan, dtype=np.uint64)
+    got_host = np.zeros(g.nchan, dtype=np.float32)
+    got_map = np.zeros(g.nchan, dtype=np.uint64)
+    for first, n in _shard_ranges(counts):
+        st = b2p.Baseband2Power(kernel=kernel, nchunk=n, first_chunk=first, nchunk_total=48, stage_ndf=16)
+        assert st.nchan == 7 * n and st.source_frame_bytes == g.frame_bytes
+        sl = slice(7 * first, 7 * (first + n))
+        st.accumulate_device([dev], ndf)              # pointer = frame 0 of the full stream
+        got_dev[sl] = st.read_sums()[0]
+        st.reset()
+        got_host[sl] = st.integrate_host([pin], ndf)[0]
+        st.accumulate_host_mapped([pin], ndf)
+        got_map[sl] = st.read_sums()[0]
+        st.close()
+    assert np.array_equal(got_dev, want)
+    assert np.array_equal(got_map, want)
+    assert np.array_equal(got_host.view(np.uint32), oracle_mod.finish(want).view(np.uint32))
+    pin.free()
+    dev.free()
+
+
+def test_shard_rejects_bad_ranges(b2p):
+    with pytest.raises(b2p.B2pError):
+        b2p.Baseband2Power(nchunk=6, first_chunk=44, nchunk_total=48)
+    with pytest.raises(b2p.B2pError):
+        b2p.Baseband2Power(nchunk=6, first_chunk=-1, nchunk_total=48)
+    with pytest.raises(b2p.B2pError):
+        b2p.ShardGroup([0, 0], [6, 6])                # does not add up to 48
+
+
+@pytest.mark.parametrize("counts", [[6] * 8, [5, 5, 5, 5, 7, 7, 7, 7], [48, 0], [20, 28]])
+def test_shard_group_on_one_gpu(b2p, oracle_mod, counts):
+    """b2p_group_*: issue on every shard, wait afterwards; here all shards share GPU 0."""
+    nbeam, ndf = 2, 90
+    blocks = [oracle_mod.synth_fill(ndf, seed=960 + b, mode=b % 2) for b in range(nbeam)]
+    pins = [b2p.PinnedBuffer(b.nbytes) for b in blocks]
+    for p, b in zip(pins, blocks):
+        p.array[:] = b
+    want = [oracle_mod.accumulate_omp(b) for b in blocks]
+    grp = b2p.ShardGroup([0] * len(counts), counts, nbeam=nbeam)
+    assert [(f, n) for _, f, n in grp.shards] == list(_shard_ranges(counts))
+    out = grp.integrate_host(pins, ndf)
+    for b in range(nbeam):
+        assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(want[b]).view(np.uint32)), b
+    # an integration over two blocks: accumulate, then integrate closes it
+    grp.accumulate_host(pins, ndf)
+    out = grp.integrate_host(pins[::-1], ndf)
+    for b in range(nbeam):
+        s = want[b] + want[nbeam - 1 - b]
+        assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(s).view(np.uint32)), b
+    grp.accumulate_host(pins, ndf)
+    out = grp.finish()
+    for b in range(nbeam):
+        assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(want[b]).view(np.uint32)), b
+    grp.close()
+    for p in pins:
+        p.free()
+
+
+def test_split_chunks_and_probe(b2p):
+    assert b2p.split_chunks(None, 8) == [6] * 8
+    assert b2p.split_chunks([23, 23, 23, 23, 35, 35, 35, 35], 8) == [5, 5, 5, 5, 7, 7, 7, 7]
+    assert sum(b2p.split_chunks([1.0, 2.5, 0.0, 3.1], 4)) == 48
+    assert b2p.split_chunks([1.0, 2.5, 0.0, 3.1], 4)[2] == 0
+    with pytest.raises(b2p.B2pError):
+        b2p.split_chunks([0.0, 0.0], 2)
+    rates = b2p.probe_h2d([0], nbytes=64 << 20, reps=2)
+    assert len(rates) == 1 and rates[0] > 1.0         # GB/s; any real link is far above this
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_async_host_path(b2p, oracle_mod, kernel):
+    """accumulate_host_async / wait_input / wait_output on two contexts driven by one thread."""
+    ndf = 64
+    blocks = [oracle_mod.synth_fill(ndf, seed=970 + i, mode=1) for i in range(2)]
+    pins = [b2p.PinnedBuffer(b.nbytes) for b in blocks]
+    for p, b in zip(pins, blocks):
+        p.array[:] = b
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(b)) for b in blocks]
+    sts = [b2p.Baseband2Power(kernel=kernel, stage_ndf=8, nstage_bufs=2) for _ in range(2)]
+    for rep in range(3):
+        for st, p in zip(sts, pins):
+            st.accumulate_host_async([p], ndf, finish=True)
+        for st in sts:
+            st.wait_input()
+        for i, st in enumerate(sts):
+            assert np.array_equal(st.wait_output()[0].view(np.uint32), want[i].view(np.uint32)), (rep, i)
+    with pytest.raises(b2p.B2pError):
+        sts[0].wait_output()                          # nothing queued any more
+    for st in sts:
+        st.close()
+    for p in pins:
+        p.free()
+
+
+def test_reset_mid_integration_then_many_tma_launches(b2p, oracle_mod):
+    """a reset that drops work must leave every device-side counter clean — run past
+    the ticket ring (4096 launches) afterwards and compare with the oracle."""
+    g = oracle_mod.Geometry()
+    ndf = 8
+    block = oracle_mod.synth_fill(ndf, seed=980, mode=1)
+    want = oracle_mod.finish(oracle_mod.accumulate(block))
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    out = b2p.DeviceBuffer(g.nchan * 4)
+    st = b2p.Baseband2Power(kernel="tma")
+    st.accumulate_device([dev], ndf)
+    st.reset()
+    for i in range(4200):
+        st.integrate_device([dev], ndf, out)
+        if i in (0, 4095, 4096, 4199):
+            b2p.device_sync(0)
+            got = out.download().view(np.float32)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), i
+    st.close()
+    dev.free()
+    out.free()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_launches_on_different_streams_are_ordered(b2p, oracle_mod, kernel):
+    """accumulate on one stream, finish on another, accumulate again on the context's
+    own stream — the library orders each launch behind the previous one."""
+    torch = pytest.importorskip("torch")
+    g = oracle_mod.Geometry()
+    ndf = 500
+    block = oracle_mod.synth_fill(ndf, seed=990, mode=1)
+    want = oracle_mod.finish(oracle_mod.accumulate_omp(block))
+    buf = torch.from_numpy(block).cuda()
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = torch.zeros(20, g.nchan, dtype=torch.float32, device="cuda")
+    st = b2p.Baseband2Power(kernel=kernel)
+    for i in range(20):
+        st.accumulate_device([buf], ndf, sa.cuda_stream)
+        st.finish_device(outs[i], sb.cuda_stream)
+        st.accumulate_device([buf], ndf, None)
+        st.finish_device(outs[i], sa.cuda_stream)
+    torch.cuda.synchronize()
+    b2p.device_sync(0)
+    res = outs.cpu().numpy()
+    for i in range(20):
+        assert np.array_equal(res[i].view(np.uint32), want.view(np.uint32)), i
+    st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("ndf", [16, 255, 256, 257, 1024, 4100])
+def test_piece_shapes(b2p, oracle_mod, kernel, ndf):
+    """Launch shapes of the host path (whole-wave split counts for short pieces)."""
+    block = oracle_mod.synth_fill(ndf, seed=ndf, mode=0)
+    want = oracle_mod.accumulate_omp(block)
+    st = b2p.Baseband2Power(kernel=kernel)
+    dev = b2p.DeviceBuffer(block.nbytes)
+    dev.upload(block)
+    st.accumulate_device([dev], ndf)
+    assert np.array_equal(st.read_sums()[0], want)
+    dev.free()
+    st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cuda_graph_of_single_launch_integration(b2p, oracle_mod, kernel):
+    torch = pytest.importorskip("torch")
+    g = oracle_mod.Geometry()
+    ndf = 96
+    blocks = [oracle_mod.synth_fill(ndf, seed=860 + i, mode=i % 2) for i in range(3)]
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(b)) for b in blocks]
+    s = torch.cuda.Stream()
+    buf = torch.from_numpy(blocks[0]).cuda()
+    out = torch.zeros(2, g.nchan, dtype=torch.float32, device="cuda")
+    st = b2p.Baseband2Power(kernel=kernel)
+    st.integrate_device([buf], ndf, out[0], s.cuda_stream)
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        cs = torch.cuda.current_stream().cuda_stream
+        st.integrate_device([buf], ndf, out[0], cs)   # two integrations per replay
+        st.integrate_device([buf], ndf, out[1], cs)
+    for rep in range(6):
+        i = rep % 3
+        buf.copy_(torch.from_numpy(blocks[i]).cuda())
+        out.zero_()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        res = out.cpu().numpy()
+        for k in range(2):
+            assert np.array_equal(res[k].view(np.uint32), want[i].view(np.uint32)), (kernel, rep, k)
+    st.close()
