@@ -8,24 +8,32 @@ paf-baseband2power.py:67) unpacked, detected and integrated into 336 float32
 continuous stream of integrations.
 
   value     kernel-only: blocks already resident in HBM (4 rotating blocks, each
-            22x larger than L2), K steps on one stream (fused kernel + reduce/finish
-            kernel per step, PDL-chained), CUDA events, max over ranks.
-  e2e       the same through the C ABI with HOST buffers: b2p_accumulate_host
-            (pinned ring block -> chunked H2D overlapped with the kernel) +
-            b2p_finish (D2H of the spectrum) inside the timed region.
+            22x larger than L2), K steps on one stream, ONE kernel launch per step
+            (b2p_integrate_device, PDL-chained), CUDA events, max over ranks.
+  e2e       the same through the C ABI with HOST buffers: b2p_integrate_host
+            (pinned ring block -> chunked H2D overlapped with the kernels -> D2H of
+            the spectrum) inside the timed region.  N > 1 also measures the
+            channel-group mode: every GPU takes a link-weighted share of the chunks
+            of every beam (strided H2D), so unequal host links finish together.
   roofline  fused kernel only, per-launch duration from CUDA events recorded on
             the launching stream inside the timed region, against the measured
             HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline  the CPU oracle (a port of the specification; the reference has no
-            kernel to time, kernel.cu:1-7) on all host cores, bounded sample.
+            kernel to time, kernel.cu:1-7) on all host cores, bounded sample —
+            the very routine `--impl reference` runs.
+  ring_e2e / live_replay  BASELINE.json configs[3]/[4]: the executables through
+            SysV rings (and loopback UDP), one pipeline per GPU on every rank.
 
 `--impl reference` times that CPU port alone (rank 0 only), same metric/config.
 Multi-GPU: one process per GPU (torchrun), beams shard by rank, no collective on
-the data path; only the spectra are gathered.
+the data path; only the spectra are gathered.  Ranks are spread over the box's
+GPUs (rank i -> GPU floor(i*D/N)) so that a partial run does not crowd one host
+bridge; the map is printed in `placement`.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -38,6 +46,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "baseband_input_throughput"
 UNIT = "GB/s"
+BLOCK_NDF = 8192
+CPU_NOTE = ("reference kernel absent (kernel.cu:1-7): C port of the specification, gcc -O3 -march=native "
+            "-fopenmp, frames handed to threads dynamically")
 
 
 def _peaks():
@@ -114,6 +125,8 @@ class ClockSampler(threading.Thread):
                 "power_w_max": round(max(self.power), 1) if self.power else None}
 
 
+# --------------------------------------------------------------------------- CPU port
+
 def _cpu_port(native=True):
     """The CPU oracle built for this host (the only place bench.py executes oracle/)."""
     import oracle
@@ -126,55 +139,114 @@ def _cpu_port(native=True):
     return oracle, (L or oracle.lib())
 
 
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port_measure(ndf: int, min_seconds: float = 4.0, min_passes: int = 50, max_seconds: float = 25.0):
+    """Time the CPU port on one beam-integration held in host RAM.  ONE routine for both the
+    `--impl reference` arm and the in-line `cpu_baseline`, so the two cannot drift apart: same
+    allocation (anonymous mmap, transparent huge pages requested, first touched by all
+    threads), same thread count (all the process may use — explicit, torchrun exports
+    OMP_NUM_THREADS=1), same policy: 3 untimed passes, then whole passes until >= min_seconds
+    AND >= min_passes (capped at max_seconds); median and best are both reported."""
+    import mmap
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+    oracle, L = _cpu_port()
+    g = oracle.Geometry()
+    nbytes = ndf * g.frame_bytes
+    mm = mmap.mmap(-1, nbytes, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+    try:
+        mm.madvise(mmap.MADV_HUGEPAGE)
+    except Exception:
+        pass
+    block = np.frombuffer(mm, dtype=np.uint8)
+    # a short synthetic piece (Gaussian, sigma 512) tiled over the block: the arithmetic has no
+    # data-dependent branch, so the content does not change the rate; the piece is 64 frames
+    piece = oracle.synth_fill(min(64, ndf), seed=1, mode=1)
+    threads = _host_threads()
+    n = piece.nbytes
+
+    def fill(i):
+        m = min(n, nbytes - i * n)
+        block[i * n:i * n + m] = piece[:m]
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:   # first touch from many threads
+        list(ex.map(fill, range((nbytes + n - 1) // n)))
+    sums = np.zeros(g.nchan, dtype=np.uint64)
+    for _ in range(3):
+        oracle.accumulate_omp(block, ndf, g, sums=sums, nthreads=threads, L=L)
+    times = []
+    t_begin = time.perf_counter()
+    while True:
+        sums[:] = 0
+        t0 = time.perf_counter()
+        oracle.accumulate_omp(block, ndf, g, sums=sums, nthreads=threads, L=L)
+        oracle.finish(sums, 1.0)
+        times.append(time.perf_counter() - t0)
+        el = time.perf_counter() - t_begin
+        if (el >= min_seconds and len(times) >= min_passes) or el >= max_seconds:
+            break
+    n1 = min(ndf, 1024)                           # one single-thread pass over 1/8 block, for the per-core figure
+    t0 = time.perf_counter()
+    oracle.accumulate(block[: n1 * g.frame_bytes], n1, g, L=L)
+    t_single = (time.perf_counter() - t0) * (ndf / n1)
+    med, best = statistics.median(times), min(times)
+    t_int = ndf * 128 * 27.0 / 32.0 * 1e-6
+    del block
+    try:
+        mm.close()
+    except BufferError:
+        pass
+    return {
+        "value": round(nbytes / med / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": (f"{len(times)} passes over 1 beam-integration of {ndf} frames ({nbytes} B) in host RAM "
+                   f"(THP-advised anonymous memory) in {round(sum(times), 1)} s; median; "
+                   f"best {round(nbytes / best / 1e9, 3)} GB/s"),
+        "best": round(nbytes / best / 1e9, 3), "passes": len(times),
+        "ms_per_pass_median": round(med * 1e3, 3),
+        "realtime_factor": round(t_int / med, 3),
+        "single_thread_GBps": round(nbytes / t_single / 1e9, 3),
+        "note": CPU_NOTE,
+    }
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The reference
     never wrote one (kernel.cu:1-7), so this is the oracle port on all host threads."""
     if rank != 0:
         return
-    import numpy as np
-    oracle, L = _cpu_port()
-    g = oracle.Geometry()
-    ndf = args.ndf
-    block = np.empty(ndf * g.frame_bytes, dtype=np.uint8)
-    gc = g.c()
-    import ctypes
-    L.b2p_oracle_synth_fill(block.ctypes.data, ndf, ctypes.byref(gc), 1, 0, 1)
-    threads = _host_threads()   # explicit: torchrun exports OMP_NUM_THREADS=1
-    sums = np.zeros(g.nchan, dtype=np.uint64)
-    for _ in range(args.warmup):
-        oracle.accumulate_omp(block, ndf, g, sums=sums, nthreads=threads, L=L)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sums[:] = 0
-        oracle.accumulate_omp(block, ndf, g, sums=sums, nthreads=threads, L=L)
-        oracle.finish(sums, 1.0)
-    dt = time.perf_counter() - t0
-    ms = dt / args.steps * 1e3
-    gbs = block.nbytes / (ms * 1e-3) / 1e9
-    t_int = ndf * 128 * 27.0 / 32.0 * 1e-6
-    sample = f"{args.steps} steps x 1 beam-integration of {ndf} frames ({block.nbytes} B) on host RAM"
-    emit(({
-        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+    # each "step" is one pass; the pass count comes from the time policy, not from --steps,
+    # so that the figure equals the b200 arm's in-line cpu_baseline on the same box
+    cpu = cpu_port_measure(args.ndf)
+    emit({
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": cpu["passes"], "warmup": 3,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": cpu["ms_per_pass_median"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": _config(args, 1),
-        "realtime_factor": round(t_int / (ms * 1e-3), 3),
-        "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample,
-                         "note": "reference kernel absent (kernel.cu:1-7): C port of the specification, gcc -O3 -march=native -fopenmp"},
-        "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        "realtime_factor": cpu["realtime_factor"],
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
 
 
 def _config(args, nbeam):
+    """Identical in both arms (the driver compares the dicts); run-specific facts — resolved
+    kernel, split count, GPU placement — live in top-level keys of the b200 line."""
     return {
         "workload": ("BASELINE.json configs[1]: single beam, continuous stream of integrations, "
                      "1 input ring block (8192 frames x 48 chunks x 7168 B = 2818572288 B) -> 336 x float32 per step"
                      if nbeam == 1 else
                      f"BASELINE.json configs[2]: {nbeam} beams batched per step, each 1 ring block of 2818572288 B"),
         "nbeam_per_gpu": nbeam, "ndf": args.ndf, "nchunk": 48, "nch_per_chunk": 7, "nsamp_df": 128,
-        "mode": "exact-uint64", "kernel": args.kernel,
+        "mode": "exact-uint64",
         "l2": "inputs larger than L2: up to 4 rotating 2.8 GB blocks per beam (value), 2 rotating pinned blocks (e2e)",
         "parallelism": f"beams sharded by rank, {args.gpus} x independent, no collective on the data path",
     }
@@ -202,11 +274,50 @@ def emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
-def _host_threads():
+def _mem_available_bytes():
     try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return None
+
+
+# --------------------------------------------------------------------------- SysV shared blocks
+
+class SysVBlock:
+    """A host block in a SysV shared-memory segment, so that every rank (one process per GPU)
+    can read every beam's ring block — what a PSRDADA ring is (shmget/shmat), minus the ring."""
+    IPC_CREAT, IPC_RMID = 0o1000, 0
+
+    def __init__(self, key: int, nbytes: int, create: bool):
+        libc = ctypes.CDLL(None, use_errno=True)
+        libc.shmget.restype = ctypes.c_int
+        libc.shmget.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
+        libc.shmat.restype = ctypes.c_void_p
+        libc.shmat.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        libc.shmdt.argtypes = [ctypes.c_void_p]
+        libc.shmctl.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        self.libc, self.nbytes, self.owner = libc, nbytes, create
+        self.id = libc.shmget(key, nbytes, (self.IPC_CREAT | 0o666) if create else 0o666)
+        if self.id < 0:
+            raise OSError(ctypes.get_errno(), f"shmget key {key:#x} ({nbytes} B)")
+        self.ptr = libc.shmat(self.id, None, 0)
+        if self.ptr in (None, ctypes.c_void_p(-1).value):
+            raise OSError(ctypes.get_errno(), "shmat")
+
+    def close(self):
+        if self.ptr:
+            self.libc.shmdt(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+        if self.owner and self.id >= 0:
+            self.libc.shmctl(self.id, self.IPC_RMID, None)
+            self.id = -1
+
+
+class Run:
+    """What the legs share: rank layout, collectives, the loaded library."""
 
 
 def main():
@@ -216,14 +327,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nbeam", type=int, default=1, help="beam streams per GPU per step")
-    ap.add_argument("--ndf", type=int, default=8192, help="data frames per ring block")
+    ap.add_argument("--ndf", type=int, default=BLOCK_NDF, help="data frames per ring block")
     ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma"])
     ap.add_argument("--nsplit", type=int, default=0, help="time splits per chunk (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 32)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ring", action="store_true", help="skip the executables-through-the-rings leg")
+    ap.add_argument("--no-live", action="store_true", help="skip the UDP live-replay leg")
+    ap.add_argument("--ring-blocks", type=int, default=64, help="integrations streamed through the rings (configs[1]: 64)")
+    ap.add_argument("--live-blocks", type=int, default=2, help="ring blocks of live UDP replay per beam")
     ap.add_argument("--beamset", type=int, default=36, help="extra kernel-only point: full beam set on one GPU (0 = skip)")
+    ap.add_argument("--placement", default="spread", choices=["spread", "identity"],
+                    help="rank -> GPU map when the box has more GPUs than ranks")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -242,20 +358,38 @@ def main():
     import torch.distributed as dist
 
     from paf_baseband2power_b200 import BMF, Baseband2Power, PinnedBuffer, device_info
+    from paf_baseband2power_b200 import _lib
+    from paf_baseband2power_b200 import api as b2p_api
+    from paf_baseband2power_b200.sharding import beams_for_rank, gather_spectra, gpu_for_rank
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
-    torch.cuda.set_device(local)
+    ngpu_box = torch.cuda.device_count()
+    env_map = os.environ.get("B2P_BENCH_GPUS")
+    if env_map:
+        gpu_map = [int(x) for x in env_map.split(",")][:world]
+    else:
+        gpu_map = [gpu_for_rank(r, world, ngpu_box, args.placement) for r in range(world)]
+    gpu = gpu_map[local] if local < len(gpu_map) else local
+    torch.cuda.set_device(gpu)
     host_pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", gpu))
         host_pg = dist.new_group(backend="gloo")   # spectra are gathered host-side, 1344 B per beam
+
+    R = Run()
+    R.args, R.rank, R.world, R.gpu, R.host_pg = args, rank, world, gpu, host_pg
+    R.vcpus = _host_threads()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_pg)
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -264,36 +398,54 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_gather_floats(x: float) -> list:
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def gather_objects(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world if rank == 0 else None
+        dist.gather_object(obj, out, dst=0, group=host_pg)
+        return out
+
+    R.barrier, R.host_barrier, R.max_over_ranks, R.gather_objects = barrier, host_barrier, max_over_ranks, gather_objects
+
     nbeam, ndf = args.nbeam, args.ndf
     g = BMF
     blk = ndf * g.frame_bytes
+    R.g, R.ndf, R.blk = g, ndf, blk
     # rotate between distinct blocks so that no step can find its input in L2 (126 MB); one
     # set is already 22x L2 per beam, so fewer sets are used when many beams fill the HBM
-    nrot = max(1, min(4, int(0.45 * torch.cuda.get_device_properties(local).total_memory // (nbeam * blk))))
+    nrot = max(1, min(4, int(0.45 * torch.cuda.get_device_properties(gpu).total_memory // (nbeam * blk))))
     # ---- device-resident inputs: nrot distinct blocks per beam ----
     dev_in = torch.empty(nrot * nbeam * blk, dtype=torch.uint8, device="cuda")
-    from paf_baseband2power_b200 import _lib
     lib = _lib.load()
+    R.lib, R.dev_in = lib, dev_in
     wpb = blk // 8
     for r in range(nrot):
         for b in range(nbeam):
             beam_id = rank * nbeam + b
-            rc = lib.b2p_synth_fill_device(local, dev_in.data_ptr() + (r * nbeam + b) * blk, ndf, 48, 7, 128, 1,
+            rc = lib.b2p_synth_fill_device(gpu, dev_in.data_ptr() + (r * nbeam + b) * blk, ndf, 48, 7, 128, 1,
                                            1000 + beam_id, r * wpb, 1, None)
             assert rc == 0
     out_dev = torch.empty(nbeam * g.nchan, dtype=torch.float32, device="cuda")
-    st = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel, nsplit=args.nsplit)
+    st = Baseband2Power(device_id=gpu, nbeam=nbeam, kernel=args.kernel, nsplit=args.nsplit)
     # The kernels run on the context's own stream (stream=None through the C ABI): only
     # there may a fused kernel start under the tail of its predecessor (PDL).  torch wraps
     # that same stream so the torch.cuda.Event pair below is recorded on it.
-    xstream = torch.cuda.ExternalStream(st.stream, device=torch.device("cuda", local))
+    xstream = torch.cuda.ExternalStream(st.stream, device=torch.device("cuda", gpu))
     ptrs = [[dev_in.data_ptr() + (r * nbeam + b) * blk for b in range(nbeam)] for r in range(nrot)]
     torch.cuda.synchronize()
 
     def step(i):
         st.integrate_device(ptrs[i % nrot], ndf, out_dev, None)   # ONE launch per integration
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(gpu)
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -325,17 +477,19 @@ def main():
 
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
+    e2e_last = None
+    pinned = None
+    ke = args.e2e_steps or min(args.steps, 32)
+    R.ke = ke
     if not args.no_e2e:
-        ke = args.e2e_steps or min(args.steps, 32)
         hrot = 2
         pinned = [[PinnedBuffer(blk) for _ in range(nbeam)] for _ in range(hrot)]
         for r in range(hrot):
             for b in range(nbeam):
-                rc = lib.b2p_memcpy_d2h(local, pinned[r][b].ptr, dev_in.data_ptr() + (r * nbeam + b) * blk, blk)
+                rc = lib.b2p_memcpy_d2h(gpu, pinned[r][b].ptr, dev_in.data_ptr() + (r * nbeam + b) * blk, blk)
                 assert rc == 0
-        from paf_baseband2power_b200.sharding import beams_for_rank, gather_spectra
         my_beams = beams_for_rank(world * nbeam, rank, world)
-        ste = Baseband2Power(device_id=local, nbeam=nbeam, kernel=args.kernel)
+        ste = Baseband2Power(device_id=gpu, nbeam=nbeam, kernel=args.kernel)
 
         def e2e_step(i):
             sp = ste.integrate_host(pinned[i % hrot], ndf)   # H2D pieces + kernels + D2H of the spectra
@@ -345,38 +499,52 @@ def main():
             return sp, sp
 
         for i in range(3):
-            spec, _ = e2e_step(i)
-        # plain pinned H2D of one block: the link ceiling the e2e number sits under
-        link0, link1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stage_t = torch.empty(blk, dtype=torch.uint8, device="cuda")
-        hsrc = torch.from_numpy(pinned[0][0].array)
-        stage_t.copy_(hsrc, non_blocking=True)
-        torch.cuda.synchronize()
-        link0.record()
-        for _ in range(3):
-            stage_t.copy_(hsrc, non_blocking=True)
-        link1.record()
-        torch.cuda.synchronize()
-        h2d_link = 3 * blk / (link0.elapsed_time(link1) * 1e-3) / 1e9
-        del stage_t
+            spec, allspec = e2e_step(i)
+        # plain pinned H2D with every rank copying at once: the link ceiling the e2e number sits under
+        host_barrier()
+        h2d_link = b2p_api.probe_h2d([gpu], nbytes=1 << 30, reps=3)[0]
+        links = all_gather_floats(h2d_link)
         barrier()
         t0 = time.perf_counter()
         for i in range(ke):
-            spec, _ = e2e_step(i)
+            spec, allspec = e2e_step(i)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
         e2e_ms = max_over_ranks(dt * 1e3) / ke
-        e2e = {"value": round(world * nbeam * blk / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT,
+        by_beam = round(world * nbeam * blk / (e2e_ms * 1e-3) / 1e9, 3)
+        e2e = {"value": by_beam, "unit": UNIT,
                "h2d_bytes_per_step": nbeam * blk, "d2h_bytes_per_step": nbeam * g.out_bytes,
                "ms_per_step": round(e2e_ms, 3), "steps": ke, "host_threads_per_gpu": 1,
-               "realtime_factor": round(world * nbeam * g.t_integration_s * ndf / 8192 / (e2e_ms * 1e-3), 2),
+               "mode": "by_beam",
+               "realtime_factor": round(world * nbeam * g.t_integration_s * ndf / BLOCK_NDF / (e2e_ms * 1e-3), 2),
                "h2d_link_GBps_per_gpu": round(h2d_link, 2),
+               "h2d_link_GBps_all_ranks": [round(x, 2) for x in links],
+               "h2d_links_sum_GBps": round(sum(links), 2),
                "frac_of_h2d_link": round(nbeam * blk / (e2e_ms * 1e-3) / 1e9 / h2d_link, 4),
-               "path": "b2p_accumulate_host (pinned ring block, 256-frame pieces, 3 staging buffers) + b2p_finish"
+               "frac_of_h2d_links_sum": round(by_beam / sum(links), 4),
+               "path": "b2p_integrate_host (pinned ring block, 256-frame pieces, 3 staging buffers, one launch per piece, spectrum D2H)"
                        + (" + gloo gather of spectra to rank 0" if world > 1 else "")}
         e2e_last = spec[0].copy()
         ste.close()
+
+        # ---- N > 1: channel-group mode, link-weighted (unequal host links finish together) ----
+        if world > 1 and nbeam == 1:
+            e2e["by_beam"] = {"value": by_beam, "ms_per_step": round(e2e_ms, 3)}
+            try:
+                cg = _channel_group_e2e(R, links, allspec, (ke - 1) % hrot)
+            except SystemExit:
+                raise
+            except Exception as e:   # the by-beam figure stands
+                cg = {"error": repr(e)[:300]}
+            e2e["by_channel_group"] = cg
+            best = cg.get("all_beams") or {}
+            if best.get("value", 0) > e2e["value"]:
+                e2e.update({"value": best["value"], "ms_per_step": best["ms_per_step"], "steps": best["steps"],
+                            "mode": "by_channel_group",
+                            "realtime_factor": round(world * g.t_integration_s * ndf / BLOCK_NDF / (best["ms_per_step"] * 1e-3), 2),
+                            "frac_of_h2d_links_sum": round(best["value"] / sum(links), 4),
+                            "path": best["path"]})
     clocks = sampler.stop()
 
     # ---- CPU baseline + parity check against the oracle (rank 0, N=1 only) ----
@@ -387,61 +555,51 @@ def main():
         og = oracle.Geometry()
         if args.no_e2e:
             host = np.empty(blk, dtype=np.uint8)
-            lib.b2p_memcpy_d2h(local, host.ctypes.data, dev_in.data_ptr() + ((args.steps - 1) % nrot) * nbeam * blk, blk)
+            lib.b2p_memcpy_d2h(gpu, host.ctypes.data, dev_in.data_ptr() + ((args.steps - 1) % nrot) * nbeam * blk, blk)
             check_against = last_out
         else:
-            host = pinned[(ke - 1) % hrot][0].array
+            host = pinned[(ke - 1) % 2][0].array
             check_against = e2e_last
-        threads = _host_threads()
-        times = []
-        t_begin = time.perf_counter()
-        while True:
-            sums = np.zeros(og.nchan, dtype=np.uint64)
-            t0 = time.perf_counter()
-            oracle.accumulate_omp(host, ndf, og, sums=sums, nthreads=threads, L=L)
-            times.append(time.perf_counter() - t0)
-            if time.perf_counter() - t_begin > 10.0 or len(times) >= 200:
-                break
-        t0 = time.perf_counter()                      # one single-thread pass, for the per-core figure
-        oracle.accumulate(host, ndf, og, L=L)
-        t_single = time.perf_counter() - t0
+        sums = oracle.accumulate_omp(host, ndf, og, nthreads=R.vcpus, L=L)
         want = oracle.finish(sums, 1.0)
         parity = bool(np.array_equal(want.view(np.uint32), check_against.view(np.uint32)))
-        med = statistics.median(times)
-        cpu = {"value": round(blk / med / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{len(times)} passes over 1 beam-integration ({blk} B) in host RAM, median; best {round(blk / min(times) / 1e9, 3)} GB/s",
-               "realtime_factor": round(g.t_integration_s * ndf / 8192 / med, 3),
-               "single_thread_GBps": round(blk / t_single / 1e9, 3),
-               "note": "reference kernel absent (kernel.cu:1-7): C port of the specification, gcc -O3 -march=native -fopenmp"}
         if not parity:
             raise SystemExit("bench.py: GPU spectrum differs from the CPU oracle — number withheld")
+        del host
+    if pinned is not None:
+        for row in pinned:
+            for p in row:
+                p.free()
+        pinned = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_port_measure(ndf)               # the routine `--impl reference` runs
 
-    # ---- extra: the same stream through the real process surface (SysV rings + executables) ----
+    # ---- configs[1]/[3]: the same stream through the real process surface, on EVERY rank ----
+    # (SysV rings + executables, one pipeline and one ring pair per GPU: paf-baseband2power.py:88-95,114-115)
     ring = None
-    if rank == 0 and world == 1 and not args.no_e2e and not args.no_ring and nbeam == 1:
-        try:
-            import importlib.util
-            spec_ = importlib.util.spec_from_file_location("run_ring_e2e", os.path.join(ROOT, "tools", "run_ring_e2e.py"))
-            mod = importlib.util.module_from_spec(spec_)
-            spec_.loader.exec_module(mod)
-            ring = mod.run(ndf=ndf, nbufs=4, nblocks=16, gpu=local, kernel=args.kernel)
-        except Exception as e:  # informational leg only
-            ring = {"error": repr(e)[:300]}
+    if not args.no_e2e and not args.no_ring and nbeam == 1:
+        ring = _ring_leg(R)
+
+    # ---- configs[4]: UDP live-rate replay, one beam per GPU on every rank ----
+    live = None
+    if not args.no_e2e and not args.no_live and nbeam == 1:
+        live = _live_leg(R)
 
     # ---- extra: full beam set on one GPU, kernel-only (configs[2]) ----
     beamset = None
-    if args.beamset and nbeam == 1 and args.beamset > 1:
+    if args.beamset and nbeam == 1 and args.beamset > 1 and world == 1:
         try:
             nb = args.beamset
             del dev_in
+            R.dev_in = None
             torch.cuda.empty_cache()
             big = torch.empty(nb * blk, dtype=torch.uint8, device="cuda")
             for b in range(nb):
-                lib.b2p_synth_fill_device(local, big.data_ptr() + b * blk, ndf, 48, 7, 128, 1, 2000 + rank * nb + b, 0, 1, None)
+                lib.b2p_synth_fill_device(gpu, big.data_ptr() + b * blk, ndf, 48, 7, 128, 1, 2000 + rank * nb + b, 0, 1, None)
             bout = torch.empty(nb * g.nchan, dtype=torch.float32, device="cuda")
-            sb = Baseband2Power(device_id=local, nbeam=nb, kernel=args.kernel)
+            sb = Baseband2Power(device_id=gpu, nbeam=nb, kernel=args.kernel)
             bp = [big.data_ptr() + b * blk for b in range(nb)]
-            bx = torch.cuda.ExternalStream(sb.stream, device=torch.device("cuda", local))
+            bx = torch.cuda.ExternalStream(sb.stream, device=torch.device("cuda", gpu))
             for _ in range(3):
                 sb.integrate_device(bp, ndf, bout, None)
             barrier()
@@ -470,26 +628,231 @@ def main():
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs: copy, read+write)",
                 "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                "traffic_source": ((tr or {}).get("source", "profiles/roofline_traffic.json")
+                                   + " (ncu --set full capture of this kernel, not this run)") if tr else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel": f"b2p_fused_{st.kernel}_bmf",
                 "launch_ms": round(per_launch_ms, 5), "launches_timed": fused_n,
-                "timing": "isolated per-launch CUDA events on the launching stream, second pass of K steps",
+                "timing": "isolated per-launch CUDA events on the launching stream, second pass of K steps "
+                          "(the launch includes the cross-CTA reduce and the float32 finish)",
                 "achieved_in_stream": round(alg_bytes / (ms_step * 1e-3) / 1e9, 1),
                 "frac_of_nominal_8000": round(achieved / 8000.0, 4)}
     if rank == 0:
-        emit(({
+        emit({
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
-            "data": "synthetic", "config": _config(args, nbeam) | {"kernel": st.kernel, "nsplit": st.nsplit},
-            "realtime_factor": round(world * nbeam * g.t_integration_s * ndf / 8192 / (ms_step * 1e-3), 1),
+            "data": "synthetic", "config": _config(args, nbeam),
+            "kernel_info": {"kernel": st.kernel, "nsplit": st.nsplit,
+                            "launches_per_integration": launches / args.steps},
+            "placement": {"policy": "env B2P_BENCH_GPUS" if env_map else args.placement, "gpus_on_box": ngpu_box,
+                          "rank_to_gpu": gpu_map, "host_vcpus": R.vcpus,
+                          "host_mem_available_GB": round((_mem_available_bytes() or 0) / 1e9, 1)},
+            "realtime_factor": round(world * nbeam * g.t_integration_s * ndf / BLOCK_NDF / (ms_step * 1e-3), 1),
             "samples_per_s": round(world * nbeam * ndf * 128 * g.nchan / (ms_step * 1e-3), 1),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "parity_vs_oracle": parity,
-            "ring_e2e": ring, "beamset": beamset, "device": device_info(local)["name"],
-        }))
+            "ring_e2e": ring, "live_replay": live, "beamset": beamset, "device": device_info(gpu)["name"],
+        })
     st.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- legs (N-rank aware)
+
+def _channel_group_e2e(R, links, by_beam_spec, src_rot):
+    """Every GPU takes chunks [first_r, first_r + n_r) of EVERY beam, n_r in proportion to its
+    measured host-link rate; the blocks live in SysV shared memory (as ring blocks do) and are
+    page-locked by every rank.  Returns timings for one beam over N GPUs and for N beams."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from paf_baseband2power_b200 import Baseband2Power
+    from paf_baseband2power_b200 import api as b2p_api
+    from paf_baseband2power_b200.sharding import gather_channel_groups
+    rank, world, gpu, lib, blk, ndf, g, args = R.rank, R.world, R.gpu, R.lib, R.blk, R.ndf, R.g, R.args
+
+    base = [0]
+    if rank == 0:
+        base[0] = 0x5B200000 | ((os.getpid() & 0xFFF) << 8)
+    dist.broadcast_object_list(base, src=0, group=R.host_pg)
+    mine = SysVBlock(base[0] + rank, blk, create=True)
+    # the block the by-beam loop finished on, so that the two modes can be compared bit for bit
+    rc = lib.b2p_memcpy_d2h(gpu, mine.ptr, R.dev_in.data_ptr() + src_rot * blk, blk)
+    assert rc == 0
+    R.host_barrier()
+    blocks = [mine if r == rank else SysVBlock(base[0] + r, blk, create=False) for r in range(world)]
+    t_reg = time.perf_counter()
+    for b in blocks:
+        rc = lib.b2p_host_register(b.ptr, blk)
+        assert rc == 0, "cudaHostRegister of a shared beam block failed"
+    t_reg = time.perf_counter() - t_reg
+    counts = b2p_api.split_chunks(links, world, 48)
+    first = sum(counts[:rank])
+    out = {"link_GBps": [round(x, 2) for x in links], "chunks_per_gpu": counts,
+           "register_s_per_rank": round(t_reg, 2),
+           "host_blocks": "SysV shared memory, one 2.8 GB block per beam, page-locked by every rank"}
+
+    def run_mode(nb, steps):
+        ctx = None
+        if counts[rank] > 0:
+            ctx = Baseband2Power(device_id=gpu, nbeam=nb, kernel=args.kernel, nchunk=counts[rank],
+                                 first_chunk=first, nchunk_total=48)
+        ptrs = [blocks[b].ptr for b in range(nb)]
+
+        def one():
+            sp = np.zeros((nb, 0), dtype=np.float32)
+            if ctx is not None:
+                ctx.accumulate_host_async(ptrs, ndf, finish=True)
+                sp = ctx.wait_output()                          # [nb][counts[rank]*7]
+            return gather_channel_groups(sp, counts, 7, group=R.host_pg)   # 1344 B per beam per rank
+
+        for _ in range(2):
+            full = one()
+        R.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            full = one()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        R.barrier()
+        ms = R.max_over_ranks(dt * 1e3) / steps
+        ok = None
+        if rank == 0 and by_beam_spec is not None:
+            ok = bool(np.array_equal(full.view(np.uint32), np.asarray(by_beam_spec)[:nb].view(np.uint32)))
+        if ctx is not None:
+            ctx.close()
+        return {"beams_per_step": nb, "value": round(nb * blk / (ms * 1e-3) / 1e9, 3), "unit": UNIT,
+                "ms_per_step": round(ms, 3), "steps": steps,
+                "realtime_factor": round(nb * g.t_integration_s * ndf / BLOCK_NDF / (ms * 1e-3), 2),
+                "bit_identical_to_by_beam_spectra": ok,
+                "path": f"b2p_accumulate_host_async + b2p_wait_output on one chunk-group shard per GPU (strided H2D, "
+                        f"pitch 344064 B; chunks per GPU {counts} from the measured link rates) + gloo gather of the channel ranges"}
+
+    try:
+        out["single_beam"] = run_mode(1, max(4, R.ke))      # one beam's block over N host links
+        out["all_beams"] = run_mode(world, max(4, R.ke // 2))
+        if rank == 0:
+            for k in ("single_beam", "all_beams"):
+                if out[k]["bit_identical_to_by_beam_spectra"] is False:
+                    raise SystemExit("bench.py: channel-group spectra differ from the by-beam spectra — number withheld")
+    finally:
+        for b in blocks:
+            lib.b2p_host_unregister(b.ptr)
+        R.host_barrier()
+        for b in blocks:
+            b.close()
+    return out
+
+
+def _load_tool(name):
+    import importlib.util
+    spec_ = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mod)
+    return mod
+
+
+def _ring_plan(world, want_bufs, blk_ndf):
+    """Ring geometry that fits the host: the reference block (8192 frames, 2.8 GB) when
+    memory allows, else shorter blocks with the integration spanning several (-n 8192)."""
+    avail = _mem_available_bytes()
+    ndf_blk, nbufs = blk_ndf, want_bufs
+    frame = 48 * 7168
+    while avail is not None and world * nbufs * ndf_blk * frame > 0.6 * avail and ndf_blk > 512:
+        ndf_blk //= 2
+    return ndf_blk, nbufs, avail
+
+
+def _ring_leg(R):
+    from paf_baseband2power_b200.sharding import ring_keys_for_beam
+    rank, world, gpu, args, ndf = R.rank, R.world, R.gpu, R.args, R.ndf
+    try:
+        mod = _load_tool("run_ring_e2e")
+        ndf_blk, nbufs, _ = _ring_plan(world, 3, ndf)
+        per_int = ndf // ndf_blk
+        salt = (os.getppid() & 0x3F) * 0x10000
+        keys = ring_keys_for_beam(rank, 0x1B200 + salt, 0x1B2A0 + salt, 0x100)
+        res = mod.run(ndf=ndf_blk, nbufs=nbufs, nblocks=args.ring_blocks * per_int, gpu=gpu, kernel=args.kernel,
+                      keys=keys, ndf_integration=ndf if per_int > 1 else 0,
+                      producer_threads=max(1, R.vcpus // world), seed=1 + rank, start_barrier=R.host_barrier)
+        res.pop("_spectra", None)
+        res["rank"] = rank
+    except Exception as e:
+        res = {"rank": rank, "error": repr(e)[:300]}
+        try:
+            R.host_barrier()
+        except Exception:
+            pass
+    allres = R.gather_objects(res)
+    if rank != 0:
+        return None
+    good = [r for r in allres if "error" not in r]
+    out = {"path": "paf_memdb -> ring -> paf_baseband2power -> ring -> paf_dbdisk: one pipeline and one ring pair per GPU, all running at once",
+           "integrations_per_beam": args.ring_blocks, "pipelines": len(allres)}
+    if good:
+        busy = max(r["stage_busy_s"] for r in good)
+        total = sum(r["blocks"] * r["ndf_per_block"] * 48 * 7168 for r in good)
+        t_data = sum(r["blocks"] * r["ndf_per_block"] * 128 * 27.0 / 32.0 * 1e-6 for r in good)
+        out.update({"aggregate_GBps": round(total / busy / 1e9, 3),
+                    "aggregate_realtime_factor": round(t_data / busy, 2),
+                    "slowest_stage_busy_s": busy,
+                    "per_rank_GBps": [r.get("stage_GBps") for r in allres]})
+        if world == 1:                              # same keys as in round 1's line
+            out.update({k: v for k, v in good[0].items() if k not in ("rank",)})
+    out["per_rank"] = allres
+    return out
+
+
+def _live_leg(R):
+    from paf_baseband2power_b200.sharding import ring_keys_for_beam
+    rank, world, gpu, args, ndf = R.rank, R.world, R.gpu, R.args, R.ndf
+    try:
+        mod = _load_tool("run_live_replay")
+    except Exception as e:
+        return {"error": repr(e)[:300]} if rank == 0 else None
+    ndf_blk, nbufs, _ = _ring_plan(world, 4, ndf)
+    per_int = ndf // ndf_blk
+    threads = max(1, min(6, R.vcpus // (2 * world)))
+    trials = []
+    for ti, rate in enumerate((1.0, 0.5, 0.25)):
+        salt = (os.getppid() & 0x3F) * 0x10000 + ti * 0x1000
+        keys = ring_keys_for_beam(rank, 0x2C200 + salt, 0x2C2A0 + salt, 0x100)
+        try:
+            res = mod.run(ndf=ndf_blk, nblocks=args.live_blocks * per_int, rate_frac=rate, threads=threads, gpu=gpu,
+                          keys=keys, port=21000 + 64 * rank + 8 * ti, nbufs=nbufs,
+                          ndf_integration=ndf if per_int > 1 else 0, start_barrier=R.host_barrier)
+            res["rank"] = rank
+        except Exception as e:
+            res = {"rank": rank, "error": repr(e)[:300]}
+        allres = R.gather_objects(res)
+        done = [True]
+        if rank == 0:
+            good = [r for r in allres if "error" not in r and "packets_expected" in r]
+            exp = sum(r["packets_expected"] for r in good)
+            got = sum(r["packets_received"] for r in good)
+            zf = sum(r["packets_zero_filled"] for r in good)
+            ok = bool(exp) and len(good) == len(allres)
+            trials.append({"rate_x_line": rate, "beams": len(allres), "beams_ok": len(good),
+                           "packets_expected": exp, "packets_received": got, "packets_zero_filled": zf,
+                           "received_frac": round(got / exp, 5) if exp else None,
+                           "sustained_realtime_factor": rate if (ok and zf == 0) else None,
+                           "aggregate_wire_GBps": round(sum(r.get("replay_GBps", 0.0) for r in good), 2),
+                           "gpu_stage_headroom_x_realtime": [r.get("stage_headroom_x_realtime") for r in allres],
+                           "per_rank": allres})
+            done[0] = ok and got >= 0.999 * exp
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(done, src=0, group=R.host_pg)
+        if done[0]:
+            break
+    if rank != 0:
+        return None
+    return {"path": "bmf_replay -> UDP loopback -> paf_capture -> ring -> paf_baseband2power -> ring -> paf_dbdisk: one beam per GPU, all running at once",
+            "host_vcpus": R.vcpus, "sender_threads_per_beam": threads, "blocks_per_beam": args.live_blocks,
+            "line_rate": "9259 frames/s x 48 packets of 7232 B = 3.21 GB/s per beam (capture.h:27-32)",
+            "note": "loopback UDP is two kernel copies per packet on the host CPUs: this leg measures the host, the GPU stage idles",
+            "trials": trials}
 
 
 if __name__ == "__main__":

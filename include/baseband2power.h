@@ -34,6 +34,9 @@ extern "C" {
 struct dada_hdu_t;
 struct multilog_t;
 struct b2p_ctx;
+struct b2p_group;
+
+#define B2P_STAGE_MAX_GPUS 16
 
 typedef struct conf_t {
   /* the reference's fields (baseband2power.cuh:18-23) */
@@ -47,10 +50,18 @@ typedef struct conf_t {
   uint64_t ndf_integration; /* frames per integration; 0 = frames of one input block */
   int kernel;               /* B2P_KERNEL_* */
   int pin_ring;             /* page-lock the input ring (default 1) */
+  /* channel-group sharding of this beam over several GPUs (-d 0,1,2,3): GPU gpus[i] takes
+     gpu_chunks[i] consecutive chunks; all zero = split in proportion to the measured
+     host-link rate of each GPU.  ngpu <= 1: the reference's one GPU per stage process
+     (paf_baseband2power.cu:23-26). */
+  int ngpu;
+  int gpus[B2P_STAGE_MAX_GPUS];
+  int gpu_chunks[B2P_STAGE_MAX_GPUS];
   /* runtime state */
   struct dada_hdu_t *hdu_in, *hdu_out;
   struct multilog_t *log;
-  struct b2p_ctx *ctx;
+  struct b2p_ctx *ctx;      /* ngpu <= 1 */
+  struct b2p_group *grp;    /* ngpu > 1 */
   uint64_t rbufsz_in, rbufsz_out, ndf_block;
   int ring_pinned;
   /* statistics */

@@ -120,11 +120,17 @@ int b2p_oracle_accumulate_omp(const uint8_t *block, uint64_t ndf, const b2p_orac
   uint64_t *priv = (uint64_t *)calloc((size_t)nthreads * nchan, sizeof(uint64_t));
   if (!priv) return 3;
   const uint64_t fb = b2p_oracle_frame_bytes(g);
+  /* runs of 32 frames handed out dynamically: a vCPU that loses its time slice (shared
+     hosts) delays one run, not a whole 1/nthreads share of the block */
+  const uint64_t run = 32, nruns = (ndf + run - 1) / run;
 #pragma omp parallel num_threads(nthreads)
   {
-    int tid = omp_get_thread_num(), nt = omp_get_num_threads();
-    uint64_t f0 = ndf * (uint64_t)tid / nt, f1 = ndf * (uint64_t)(tid + 1) / nt;
-    b2p_oracle_accumulate(block + f0 * fb, f1 - f0, g, priv + (size_t)tid * nchan);
+    const int tid = omp_get_thread_num();
+#pragma omp for schedule(dynamic, 1)
+    for (uint64_t r = 0; r < nruns; ++r) {
+      const uint64_t f0 = r * run, n = (ndf - f0 < run) ? ndf - f0 : run;
+      b2p_oracle_accumulate(block + f0 * fb, n, g, priv + (size_t)tid * nchan);
+    }
   }
   for (int t = 0; t < nthreads; ++t)
     for (int k = 0; k < nchan; ++k) sums[k] += priv[(size_t)t * nchan + k];

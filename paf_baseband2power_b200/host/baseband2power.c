@@ -46,6 +46,7 @@ void default_baseband2power(conf_t *conf)
   conf->ndf_integration = 0;
   conf->kernel = B2P_KERNEL_AUTO;
   conf->pin_ring = 1;
+  conf->ngpu = 0;
 }
 
 static double now_s(void)
@@ -115,7 +116,31 @@ int init_baseband2power(conf_t *conf)
   p.kernel = conf->kernel;
   p.nbeam = 1;
   p.scale = conf->average ? (float)(1.0 / ((double)conf->ndf_integration * conf->nsamp_df)) : 1.0f;
-  if (b2p_create(&conf->ctx, &p) != B2P_OK) {
+  if (conf->ngpu > 1) {
+    /* one beam over several GPUs by channel group: split the chunks in proportion to what
+       each GPU's host link delivers with all of them copying at once, unless told */
+    int given = 0;
+    for (int i = 0; i < conf->ngpu; ++i) given += conf->gpu_chunks[i];
+    if (given == 0) {
+      double rate[B2P_STAGE_MAX_GPUS];
+      if (b2p_probe_h2d(conf->gpus, conf->ngpu, (size_t)256 << 20, 4, rate) != B2P_OK ||
+          b2p_split_chunks(rate, conf->ngpu, conf->nchunk, conf->gpu_chunks) != B2P_OK) {
+        STAGE_ERR(conf, "host-link probe failed: %s\n", b2p_last_error(NULL));
+        return EXIT_FAILURE;
+      }
+      if (conf->log)
+        for (int i = 0; i < conf->ngpu; ++i)
+          multilog(conf->log, LOG_INFO, "gpu %d: host link %.1f GB/s -> %d chunks\n", conf->gpus[i],
+                   rate[i], conf->gpu_chunks[i]);
+    } else if (given != conf->nchunk) {
+      STAGE_ERR(conf, "Chunk counts per GPU add up to %d, not %d\n", given, conf->nchunk);
+      return EXIT_FAILURE;
+    }
+    if (b2p_group_create(&conf->grp, &p, conf->gpus, conf->gpu_chunks, conf->ngpu) != B2P_OK) {
+      STAGE_ERR(conf, "b2p_group_create failed: %s\n", b2p_last_error(NULL));
+      return EXIT_FAILURE;
+    }
+  } else if (b2p_create(&conf->ctx, &p) != B2P_OK) {
     STAGE_ERR(conf, "b2p_create failed: %s\n", b2p_last_error(NULL));
     return EXIT_FAILURE;
   }
@@ -128,9 +153,10 @@ int init_baseband2power(conf_t *conf)
   }
   if (conf->log)
     multilog(conf->log, LOG_INFO,
-             "baseband2power ready: gpu %d, %lu frames/block, %lu frames/integration, ring %s\n",
-             conf->device_id, (unsigned long)conf->ndf_block, (unsigned long)conf->ndf_integration,
-             conf->ring_pinned ? "pinned" : "pageable");
+             "baseband2power ready: gpu %d (%d gpu%s), %lu frames/block, %lu frames/integration, ring %s\n",
+             conf->ngpu > 1 ? conf->gpus[0] : conf->device_id, conf->ngpu > 1 ? conf->ngpu : 1,
+             conf->ngpu > 1 ? "s, channel groups" : "", (unsigned long)conf->ndf_block,
+             (unsigned long)conf->ndf_integration, conf->ring_pinned ? "pinned" : "pageable");
   return EXIT_SUCCESS;
 }
 
@@ -194,8 +220,11 @@ int do_baseband2power(conf_t *conf)
       const void *ptr = blk + done * frame_bytes;
       const int closes = in_integration + n == conf->ndf_integration;
       if (!closes) {
-        if (b2p_accumulate_host(conf->ctx, &ptr, n) != B2P_OK) {
-          STAGE_ERR(conf, "b2p_accumulate_host failed: %s\n", b2p_last_error(conf->ctx));
+        const int rc = conf->grp ? b2p_group_accumulate_host(conf->grp, &ptr, n)
+                                 : b2p_accumulate_host(conf->ctx, &ptr, n);
+        if (rc != B2P_OK) {
+          STAGE_ERR(conf, "b2p_accumulate_host failed: %s\n",
+                    conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
           return EXIT_FAILURE;
         }
       } else {
@@ -208,8 +237,11 @@ int do_baseband2power(conf_t *conf)
           STAGE_ERR(conf, "Can not open an output block\n");
           return EXIT_FAILURE;
         }
-        if (b2p_integrate_host(conf->ctx, &ptr, n, (float *)out) != B2P_OK) {
-          STAGE_ERR(conf, "b2p_integrate_host failed: %s\n", b2p_last_error(conf->ctx));
+        const int rc = conf->grp ? b2p_group_integrate_host(conf->grp, &ptr, n, (float *)out)
+                                 : b2p_integrate_host(conf->ctx, &ptr, n, (float *)out);
+        if (rc != B2P_OK) {
+          STAGE_ERR(conf, "b2p_integrate_host failed: %s\n",
+                    conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
           return EXIT_FAILURE;
         }
         ipcio_close_block_write(conf->hdu_out->data_block, conf->rbufsz_out);
@@ -224,7 +256,10 @@ int do_baseband2power(conf_t *conf)
   }
   if (in_integration) { /* an incomplete integration has the wrong scale: do not emit it */
     conf->nframes_dropped += in_integration;
-    b2p_reset(conf->ctx);
+    if (conf->grp)
+      b2p_group_reset(conf->grp);
+    else
+      b2p_reset(conf->ctx);
     if (conf->log)
       multilog(conf->log, LOG_WARNING, "dropped a trailing partial integration of %lu frames\n",
                (unsigned long)in_integration);
@@ -240,6 +275,8 @@ int destroy_baseband2power(conf_t *conf)
   if (conf->ring_pinned && conf->hdu_in) dada_cuda_dbunregister(conf->hdu_in);
   if (conf->ctx) b2p_destroy(conf->ctx);
   conf->ctx = NULL;
+  if (conf->grp) b2p_group_destroy(conf->grp);
+  conf->grp = NULL;
   if (conf->hdu_out) {
     dada_hdu_unlock_write(conf->hdu_out); /* raises end-of-data for the downstream reader */
     dada_hdu_disconnect(conf->hdu_out);

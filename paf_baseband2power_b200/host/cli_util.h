@@ -27,6 +27,21 @@ static inline void cli_copy(char *dst, size_t cap, const char *src)
   snprintf(dst, cap, "%s", src ? src : "");
 }
 
+/* "0,1,2,3" -> out[]; returns how many integers were read (at most cap) */
+static inline int cli_int_list(const char *text, int *out, int cap)
+{
+  int n = 0;
+  for (const char *p = text; p && *p && n < cap;) {
+    char *end = NULL;
+    const long v = strtol(p, &end, 10);
+    if (end == p) break;
+    out[n++] = (int)v;
+    p = (*end == ',' || *end == ':') ? end + 1 : end;
+    if (end == p && *end) break;
+  }
+  return n;
+}
+
 static inline void cli_print_lines(FILE *fp, const char *const *lines)
 {
   for (; *lines; ++lines) fprintf(fp, "%s\n", *lines);

@@ -27,7 +27,7 @@ static const char *const kUsage[] = {
     " -a  Hexadecimal shared memory key for incoming ring buffer",
     " -b  Hexadecimal shared memory key for outcoming ring buffer",
     " -c  The name of the directory in which we will record the data",
-    " -d  The index of GPU",
+    " -d  The index of GPU (extension: a list 0,1,2,3 spreads the beam's channel groups over the GPUs)",
     " -h  show help",
     "extensions:",
     " -s  0 integral over the integration (default), 1 average in time",
@@ -35,6 +35,7 @@ static const char *const kUsage[] = {
     " -k  kernel: auto | ldg | tma",
     " -e  1 big-endian samples (default), 0 little-endian",
     " -p  1 page-lock the input ring (default), 0 leave it pageable",
+    " -g  chunks per GPU for a -d list, e.g. 5,5,7,7 (default: in proportion to the host-link rates)",
     NULL};
 
 static int kernel_by_name(const char *name)
@@ -47,13 +48,16 @@ static int kernel_by_name(const char *name)
 /* returns 0 to go on, 1 to leave with EXIT_FAILURE (help or a bad option) */
 static int parse_args(int argc, char *argv[], conf_t *conf)
 {
-  for (int opt; (opt = getopt(argc, argv, "a:b:c:d:hs:n:k:e:p:")) != -1;) {
+  for (int opt; (opt = getopt(argc, argv, "a:b:c:d:hs:n:k:e:p:g:")) != -1;) {
     if (opt == 'a' || opt == 'b') {
       if (cli_hex_key(optarg, opt == 'a' ? &conf->key_in : &conf->key_out, __FILE__, __LINE__)) return 1;
     } else if (opt == 'c') {
       cli_copy(conf->dir, MSTR_LEN, optarg);
     } else if (opt == 'd') {
       conf->device_id = atoi(optarg);
+      conf->ngpu = cli_int_list(optarg, conf->gpus, B2P_STAGE_MAX_GPUS);
+    } else if (opt == 'g') {
+      cli_int_list(optarg, conf->gpu_chunks, B2P_STAGE_MAX_GPUS);
     } else if (opt == 's') {
       conf->average = atoi(optarg) != 0;
     } else if (opt == 'n') {
@@ -85,7 +89,10 @@ int main(int argc, char *argv[])
   conf.log = runtime_log;
 
   /* a container that exposes a single GPU numbers it 0 whatever -d says */
-  if (b2p_device_count() == 1) conf.device_id = 0;
+  if (b2p_device_count() == 1) {
+    conf.device_id = 0;
+    for (int i = 0; i < conf.ngpu; ++i) conf.gpus[i] = 0;
+  }
 
   int status = init_baseband2power(&conf);
   if (status == EXIT_SUCCESS) status = do_baseband2power(&conf);

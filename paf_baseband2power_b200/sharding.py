@@ -56,3 +56,82 @@ def gather_spectra(local: np.ndarray, local_beams: Sequence[int], nbeam_total: i
         ids = beams_for_rank(nbeam_total, r, world)
         out[ids] = bufs[r].numpy()[: len(ids)]
     return out
+
+
+# ---------------------------------------------------------------- placement and channel groups
+
+def gpu_for_rank(rank: int, world: int, ngpus: int, policy: str = "spread") -> int:
+    """GPU a rank (or a beam's pipeline) runs on when the box has `ngpus` GPUs.
+
+    `spread`: rank i -> GPU floor(i * ngpus / world), i.e. 4 ranks on an 8-GPU box take GPUs
+    0, 2, 4, 6 instead of 0..3 — neighbouring GPUs usually hang off the same host bridge and
+    share its bandwidth, and the end-to-end rate of this path is the host link.  `identity`:
+    rank i -> GPU i (the reference launcher's -c index, paf-baseband2power.py:26)."""
+    if ngpus <= 0:
+        return rank
+    if policy == "identity" or world >= ngpus:
+        return rank % ngpus
+    return (rank * ngpus) // world
+
+
+def chunk_ranges(counts: Sequence[int]) -> List[tuple]:
+    """[(first_chunk, nchunk)] per shard for consecutive chunk counts (zeros allowed)."""
+    out, first = [], 0
+    for n in counts:
+        if n < 0:
+            raise ValueError("negative chunk count")
+        out.append((first, int(n)))
+        first += int(n)
+    return out
+
+
+def split_chunks(weights: Sequence[float] | None, n: int, nchunk: int = 48) -> List[int]:
+    """nchunk chunks over n shards in proportion to weights (largest remainder, ties to the
+    lower index) — the host-side twin of b2p_split_chunks, for planning without a GPU."""
+    w = [1.0] * n if weights is None else [float(x) for x in weights]
+    if len(w) != n or any(x < 0 for x in w) or sum(w) <= 0:
+        raise ValueError("weights must be n non-negative numbers, not all zero")
+    share = [x / sum(w) * nchunk for x in w]
+    counts = [int(s) for s in share]
+    frac = [s - c for s, c in zip(share, counts)]
+    while sum(counts) < nchunk:
+        best = max(range(n), key=lambda i: (frac[i], -i))
+        counts[best] += 1
+        frac[best] = -1.0
+    return counts
+
+
+def gather_channel_groups(local: np.ndarray, counts: Sequence[int], nch_per_chunk: int = 7, group=None,
+                          dst: int = 0):
+    """Channel-group sharding: rank r holds spectra [nbeam, counts[r]*nch] for chunks
+    chunk_ranges(counts)[r]; returns [nbeam, sum(counts)*nch] on `dst` (None elsewhere).
+    The ranges are disjoint, so the gather is a placement, not a reduction."""
+    import torch
+    import torch.distributed as dist
+
+    ranges = chunk_ranges(counts)
+    nchan = sum(counts) * nch_per_chunk
+    local = np.ascontiguousarray(local, dtype=np.float32)
+    nbeam = local.shape[0]
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        if local.shape[1] != nchan:
+            raise ValueError("single rank must hold every channel")
+        return local.copy()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if len(counts) != world:
+        raise ValueError("one chunk count per rank")
+    first, n = ranges[rank]
+    if local.shape[1] != n * nch_per_chunk:
+        raise ValueError(f"rank {rank} holds {local.shape[1]} channels, its range has {n * nch_per_chunk}")
+    pad = np.zeros((nbeam, nchan), dtype=np.float32)          # fixed-size message: 1344 B per beam
+    pad[:, first * nch_per_chunk:(first + n) * nch_per_chunk] = local
+    t = torch.from_numpy(pad)
+    bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = np.zeros((nbeam, nchan), dtype=np.float32)
+    for r, (f, m) in enumerate(ranges):
+        sl = slice(f * nch_per_chunk, (f + m) * nch_per_chunk)
+        out[:, sl] = bufs[r].numpy()[:, sl]
+    return out

@@ -217,6 +217,44 @@ def test_stage_options_average_and_multi_block_integration(tmp_path, oracle_mod,
     assert "partial integration of 32 frames" in (tmp_path / "paf_baseband2power.log").read_text()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus,chunks", [("0,0,0", None), ("0,0,0,0", "5,9,11,23")])
+def test_stage_spreads_channel_groups_over_a_gpu_list(tmp_path, oracle_mod, b2p, gpus, chunks):
+    """-d with a list: one beam's chunks are split over the listed GPUs (measured-link split, or
+    -g counts); every GPU reads its columns of the same ring block and the 1344-byte output
+    block is the oracle's spectrum.  On a one-GPU box all shards land on GPU 0."""
+    ndf_block, nblk = 40, 4
+    kin, kout = "%x" % _key(), "%x" % (_key() | 0x10000)
+    src = tmp_path / "in.dada"
+    run(os.path.join(BIN, "b2p_gen"), "-o", str(src), "-n", str(ndf_block * nblk), "-s", "15", "-H", HDR)
+    run(os.path.join(BIN, "paf_dada_db"), "-k", kin, "-b", str(ndf_block * FRAME), "-n", "3")
+    run(os.path.join(BIN, "paf_dada_db"), "-k", kout, "-b", "1344", "-n", "4")
+    try:
+        sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", kout, "-D", str(tmp_path), "-f", "s.dada", "-W"], stderr=subprocess.PIPE)
+        cmd = [os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", str(tmp_path), "-d", gpus, "-n", str(2 * ndf_block)]
+        if chunks:
+            cmd += ["-g", chunks]
+        stage = subprocess.Popen(cmd, stderr=subprocess.PIPE)
+        time.sleep(0.3)
+        run(os.path.join(BIN, "paf_diskdb"), "-a", kin, "-b", str(tmp_path), "-c", "in.dada", "-d", HDR, "-e", "1")
+        assert stage.wait(timeout=120) == 0, stage.stderr.read().decode()
+        assert sink.wait(timeout=60) == 0
+    finally:
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", kin)
+        run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", kout)
+    spectra = np.frombuffer((tmp_path / "s.dada").read_bytes()[4096:], dtype=np.float32).reshape(-1, 336)
+    assert spectra.shape[0] == 2
+    payload = np.fromfile(src, dtype=np.uint8)[4096:]
+    per = 2 * ndf_block * FRAME
+    for i in range(2):
+        want = oracle_mod.finish(oracle_mod.accumulate_omp(payload[i * per:(i + 1) * per]))
+        assert np.array_equal(spectra[i].view(np.uint32), want.view(np.uint32)), i
+    log = (tmp_path / "paf_baseband2power.log").read_text()
+    assert "channel groups" in log
+    if not chunks:
+        assert "host link" in log                     # the split came from the link probe
+
+
 def test_ring_is_reusable_for_a_second_observation(tmp_path):
     """Rings persist across runs in the reference's design (dada_db -p, paf-baseband2power.py:114):
     after end-of-data has been consumed, a new writer/reader pair starts a fresh observation."""

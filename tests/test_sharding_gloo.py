@@ -86,3 +86,79 @@ def test_single_process_gather_is_identity():
     local = np.arange(2 * 336, dtype=np.float32).reshape(2, 336)
     out = gather_spectra(local, [0, 1], 2)
     assert np.array_equal(out, local)
+
+
+# ------------------------------------------------ channel-group sharding (round 2)
+
+def _cg_worker(rank, world, port, counts, q):
+    import oracle
+    from paf_baseband2power_b200.sharding import chunk_ranges, gather_channel_groups
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, n = chunk_ranges(counts)[rank]
+    nbeam = 2
+    local = np.zeros((nbeam, 7 * n), np.float32)
+    for b in range(nbeam):
+        # the oracle on this rank's chunk columns only stands in for the GPU shard
+        blk = oracle.synth_fill(NDF, seed=700 + b, mode=1).reshape(NDF, 48, 7168)
+        sub = np.ascontiguousarray(blk[:, first:first + n]).reshape(-1)
+        if n:
+            gsub = oracle.Geometry(nchunk=n)
+            local[b] = oracle.finish(oracle.accumulate(sub, NDF, gsub), 1.0)
+    out = gather_channel_groups(local, counts)
+    if rank == 0:
+        q.put(out)
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [[24, 24], [20, 28], [48, 0], [10, 17, 21]])
+def test_channel_group_gather_over_gloo(counts):
+    """Every rank integrates its chunk range of the same beams; rank 0 places the disjoint
+    channel ranges side by side: equal to the oracle's spectrum of the whole block."""
+    import oracle
+    world = len(counts)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cg_worker, args=(r, world, port, counts, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([oracle.finish(oracle.accumulate(oracle.synth_fill(NDF, seed=700 + b, mode=1)), 1.0) for b in range(2)])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_split_chunks_host_twin():
+    from paf_baseband2power_b200.sharding import chunk_ranges, split_chunks
+    assert split_chunks(None, 8) == [6] * 8
+    assert split_chunks([23, 23, 23, 23, 35, 35, 35, 35], 8) == [5, 5, 5, 5, 7, 7, 7, 7]
+    assert split_chunks([55, 55], 2) == [24, 24]
+    c = split_chunks([1.0, 2.5, 0.0, 3.1], 4)
+    assert sum(c) == 48 and c[2] == 0
+    assert chunk_ranges([5, 0, 7]) == [(0, 5), (5, 0), (5, 7)]
+    for n in range(1, 17):
+        for nchunk in (1, 7, 48):
+            assert sum(split_chunks([1 + (i * 7) % 5 for i in range(n)], n, nchunk)) == nchunk
+    with pytest.raises(ValueError):
+        split_chunks([0, 0], 2)
+
+
+def test_gpu_placement_spreads_ranks():
+    from paf_baseband2power_b200.sharding import gpu_for_rank
+    assert [gpu_for_rank(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]     # two per half of an 8-GPU box
+    assert [gpu_for_rank(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [gpu_for_rank(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [gpu_for_rank(r, 1, 8) for r in range(1)] == [0]
+    assert [gpu_for_rank(r, 4, 8, "identity") for r in range(4)] == [0, 1, 2, 3]
+    assert [gpu_for_rank(r, 4, 2) for r in range(4)] == [0, 1, 0, 1]        # more beams than GPUs
+    for world in range(1, 9):
+        for ngpu in range(world, 17):
+            gpus = [gpu_for_rank(r, world, ngpu) for r in range(world)]
+            assert len(set(gpus)) == world and max(gpus) < ngpu

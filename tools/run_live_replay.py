@@ -21,22 +21,37 @@ FRAME = 48 * 7168
 LINE_FPS = 1.0 / 1.08e-4
 
 
-def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300):
-    kin = "%x" % (random.randint(0x2000, 0x6FFF) & 0xFFF0)
-    kout = "%x" % (random.randint(0x7000, 0xDFFF) & 0xFFF0)
-    port = random.randint(20000, 40000)
+def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300, keys=None, port=None,
+        nbufs=4, ndf_integration=0, start_barrier=None, settle_s=3.0):
+    """One beam: bmf_replay -> UDP loopback -> paf_capture -> ring -> paf_baseband2power -> ring ->
+    paf_dbdisk.  `keys`/`port` keep side-by-side beams (one per GPU) apart: own ring pair, own six
+    UDP ports (capture.h:22-24 has one port set per NIC; here one per beam on loopback)."""
+    if keys is None:
+        kin = "%x" % (random.randint(0x2000, 0x6FFF) & 0xFFF0)
+        kout = "%x" % (random.randint(0x7000, 0xDFFF) & 0xFFF0)
+    else:
+        kin, kout = "%x" % keys[0], "%x" % keys[1]
+    if port is None:
+        port = random.randint(20000, 40000)
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(threads)
     d = tempfile.mkdtemp(prefix="b2p_live_")
-    q = lambda *c: subprocess.run(list(c), check=True, capture_output=True, text=True, timeout=timeout)
-    q(os.path.join(BIN, "paf_dada_db"), "-k", kin, "-b", str(ndf * FRAME), "-n", "4")
+    q = lambda *c: subprocess.run(list(c), check=True, capture_output=True, text=True, timeout=timeout, env=env)
+    q(os.path.join(BIN, "paf_dada_db"), "-k", kin, "-b", str(ndf * FRAME), "-n", str(nbufs))
     q(os.path.join(BIN, "paf_dada_db"), "-k", kout, "-b", "1344", "-n", "8")
     nframes = ndf * nblocks
     try:
         sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", kout, "-D", d, "-f", "spectra.dada", "-W"], stderr=subprocess.DEVNULL)
-        stage = subprocess.Popen([os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", d, "-d", str(gpu)], stderr=subprocess.PIPE)
+        scmd = [os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", d, "-d", str(gpu)]
+        if ndf_integration:
+            scmd += ["-n", str(ndf_integration)]
+        stage = subprocess.Popen(scmd, stderr=subprocess.PIPE)
         cap = subprocess.Popen([os.path.join(BIN, "paf_capture"), "-a", kin, "-b", "1", "-c", str(ndf), "-d", "0", "-f", HDR, "-g", "none",
                                 "-i", "1340.5", "-j", repr(nframes * 1.08e-4), "-k", d, "-I", "127.0.0.1", "-p", str(port), "-t", "5"],
                                stderr=subprocess.PIPE)
-        time.sleep(3.0)   # the stage page-locks the 11 GB ring before it reads
+        time.sleep(settle_s)   # the stage page-locks the ring (GBs) before it reads
+        if start_barrier is not None:
+            start_barrier()
         rep = q(os.path.join(BIN, "bmf_replay"), "-D", "127.0.0.1", "-p", str(port), "-n", str(nframes + 64), "-s", "5",
                 "-r", repr(LINE_FPS * rate_frac), "-C", "512", "-T", str(threads))
         cap.wait(timeout=timeout)
@@ -53,7 +68,7 @@ def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300):
     s = re.search(r"END: (\d+) blocks in, (\d+) spectra out, ([0-9.]+) s busy", slog)
     r = re.search(r"(\d+) packets sent.*in ([0-9.]+) s \(([0-9.]+) frames/s, ([0-9.]+) GB/s, ([0-9.]+)x line rate", rep.stdout)
     out = {"path": "bmf_replay -> UDP loopback -> paf_capture -> ring -> paf_baseband2power -> ring -> paf_dbdisk",
-           "ndf_per_block": ndf, "blocks_requested": nblocks, "rate_frac_requested": rate_frac, "sender_threads": threads}
+           "gpu": gpu, "udp_port_base": port, "ndf_per_block": ndf, "blocks_requested": nblocks, "rate_frac_requested": rate_frac, "sender_threads": threads}
     if r:
         out.update({"packets_sent": int(r.group(1)), "replay_s": float(r.group(2)), "replay_GBps": float(r.group(4)),
                     "replay_x_line_rate": float(r.group(5))})
@@ -63,6 +78,9 @@ def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300):
                     "received_frac": round(int(m.group(2)) / max(1, int(m.group(3))), 4)})
     if s:
         out.update({"stage_blocks": int(s.group(1)), "spectra": int(s.group(2)), "stage_busy_s": float(s.group(3))})
+        t_data = int(s.group(1)) * ndf * 1.08e-4
+        if float(s.group(3)) > 0:
+            out["stage_headroom_x_realtime"] = round(t_data / float(s.group(3)), 2)
     return out
 
 

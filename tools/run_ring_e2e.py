@@ -21,9 +21,21 @@ HDR = os.path.join(PKG, "conf", "header_baseband2power.txt")
 FRAME = 48 * 7168
 
 
-def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300):
-    kin = "%x" % (random.randint(0x2000, 0x6FFF) & 0xFFF0)
-    kout = "%x" % (random.randint(0x7000, 0xDFFF) & 0xFFF0)
+def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300, keys=None,
+        ndf_integration=0, producer_threads=0, seed=1, start_barrier=None):
+    """`keys` = (key_in, key_out) integers when several pipelines run side by side (one per GPU,
+    own ring pair each — paf-baseband2power.py:114-115); `gpu` may be a list "0,1,2" (channel
+    groups over several GPUs); `ndf_integration` > ndf lets an integration span ring blocks;
+    `start_barrier()` is called once the rings exist and the stage is up, right before the
+    producer starts (so that side-by-side pipelines stream at the same time)."""
+    if keys is None:
+        kin = "%x" % (random.randint(0x2000, 0x6FFF) & 0xFFF0)
+        kout = "%x" % (random.randint(0x7000, 0xDFFF) & 0xFFF0)
+    else:
+        kin, kout = "%x" % keys[0], "%x" % keys[1]
+    env = dict(os.environ)
+    if producer_threads:
+        env["OMP_NUM_THREADS"] = str(producer_threads)   # torchrun exports OMP_NUM_THREADS=1
     blk = ndf * FRAME
     d = tempfile.mkdtemp(prefix="b2p_ring_")
     q = lambda *c: subprocess.run(list(c), check=True, capture_output=True, text=True, timeout=timeout)
@@ -32,10 +44,16 @@ def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300)
     try:
         sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", kout, "-D", d, "-f", "spectra.dada", "-W"],
                                 stderr=subprocess.DEVNULL)
-        stage = subprocess.Popen([os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", d, "-d", str(gpu),
-                                  "-k", kernel, "-p", str(pin)], stderr=subprocess.PIPE)
+        cmd = [os.path.join(BIN, "paf_baseband2power"), "-a", kin, "-b", kout, "-c", d, "-d", str(gpu),
+               "-k", kernel, "-p", str(pin)]
+        if ndf_integration:
+            cmd += ["-n", str(ndf_integration)]
+        stage = subprocess.Popen(cmd, stderr=subprocess.PIPE)
+        if start_barrier is not None:
+            start_barrier()
         t0 = time.perf_counter()
-        prod = q(os.path.join(BIN, "paf_memdb"), "-k", kin, "-n", str(nblocks), "-s", "1", "-H", HDR)
+        prod = subprocess.run([os.path.join(BIN, "paf_memdb"), "-k", kin, "-n", str(nblocks), "-s", str(seed), "-H", HDR],
+                              check=True, capture_output=True, text=True, timeout=timeout, env=env)
         rc = stage.wait(timeout=timeout)
         wall = time.perf_counter() - t0
         sink.wait(timeout=timeout)
@@ -50,7 +68,16 @@ def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300)
     gen = re.search(r"published .* in ([0-9.]+) s", prod.stderr)
     size = os.path.getsize(os.path.join(d, "spectra.dada"))
     t_int = ndf * 128 * 27.0 / 32.0 * 1e-6
+    spectra = None
+    try:
+        import numpy as np
+        spectra = np.fromfile(os.path.join(d, "spectra.dada"), dtype=np.float32, offset=4096).reshape(-1, 336)
+    except Exception:
+        pass
+    groups = re.findall(r"gpu (\d+): host link ([0-9.]+) GB/s -> (\d+) chunks", log)
     return {"path": "paf_memdb -> ring -> paf_baseband2power -> ring -> paf_dbdisk",
+            "gpu": gpu, "keys": [kin, kout], "_spectra": spectra,
+            "channel_groups": [{"gpu": int(a), "link_GBps": float(b), "chunks": int(c)} for a, b, c in groups] or None,
             "ndf_per_block": ndf, "ring_blocks": nbufs, "blocks": nin, "spectra": nout,
             "spectra_file_bytes": size, "ring_pinned": "ring pinned" in log,
             "stage_busy_s": busy, "stage_GBps": round(nin * blk / busy / 1e9, 3),
@@ -63,8 +90,10 @@ if __name__ == "__main__":
     ap.add_argument("--ndf", type=int, default=8192)
     ap.add_argument("--nbufs", type=int, default=4)
     ap.add_argument("--nblocks", type=int, default=16)
-    ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--gpu", default="0", help="GPU index, or a list 0,1,2,3 (channel groups)")
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--pin", type=int, default=1)
     a = ap.parse_args()
-    print(json.dumps(run(a.ndf, a.nbufs, a.nblocks, a.gpu, a.kernel, a.pin)))
+    res = run(a.ndf, a.nbufs, a.nblocks, a.gpu, a.kernel, a.pin)
+    res.pop("_spectra", None)
+    print(json.dumps(res))
