@@ -14,6 +14,10 @@
  *  -r frames per second (0 = unpaced; line rate is 9259.26)  -S sec  -i idf  -e epoch  -b beam
  *  -f first chunk frequency MHz  -L drop every L-th packet (loss injection)  -A source prefix [127.0]
  *  -C cache this many generated frames and repeat them (0 = all)  -T sender threads [1]
+ *  -G consecutive frames of a chunk per send call [1]; > 1 uses UDP generic segmentation
+ *     offload (UDP_SEGMENT): one system call and one trip through the stack for up to 8 packets.
+ *     On the wire (or on loopback towards a UDP_GRO receiver) the packets are the same 7232-byte
+ *     datagrams.
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -22,6 +26,7 @@
 #include <arpa/inet.h>
 #include <errno.h>
 #include <netinet/in.h>
+#include <netinet/udp.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,6 +37,11 @@
 
 #include "../../include/b2p_synth.h"
 #include "bmf_packet.h"
+
+#ifndef UDP_SEGMENT
+#define UDP_SEGMENT 103
+#endif
+#define GSO_MAX 8 /* 8 x 7232 = 57856 B, under the 65507-byte datagram limit */
 
 static double now_s(void)
 {
@@ -48,8 +58,8 @@ int main(int argc, char **argv)
   uint64_t nframes = 64, seed = 1, sec0 = 27 * 1000, idf0 = 0;
   double rate = 2000.0, freq0 = 1173.0;
   uint64_t cache = 0;
-  int nthreads = 1;
-  while ((arg = getopt(argc, argv, "D:p:P:n:s:m:r:S:i:e:b:f:L:A:C:T:h")) != -1) {
+  int nthreads = 1, gso = 1;
+  while ((arg = getopt(argc, argv, "D:p:P:n:s:m:r:S:i:e:b:f:L:A:C:T:G:h")) != -1) {
     switch (arg) {
       case 'D': snprintf(dest, sizeof(dest), "%s", optarg); break;
       case 'p': port_base = atoi(optarg); break;
@@ -67,6 +77,7 @@ int main(int argc, char **argv)
       case 'A': snprintf(prefix, sizeof(prefix), "%s", optarg); break;
       case 'C': cache = strtoull(optarg, NULL, 10); break;
       case 'T': nthreads = atoi(optarg); break;
+      case 'G': gso = atoi(optarg); break;
       default:
         fprintf(stdout, "bmf_replay -D dest -p port -P nports -n frames -s seed -m mode -r fps -S sec -i idf -e epoch -b beam -L drop_every\n");
         return EXIT_FAILURE;
@@ -127,33 +138,61 @@ int main(int argc, char **argv)
   {
     const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
     const int c_lo = nchunk * tid / nt, c_hi = nchunk * (tid + 1) / nt;
-    unsigned char *pkt = (unsigned char *)malloc(BMF_DF_SIZE);
-    for (uint64_t f = 0; f < nframes && !failed; ++f) {
-      uint64_t idf = idf0 + f, sec = sec0;
-      sec += (idf / BMF_NDF_PRD) * BMF_PRD_SEC; /* the frame counter wraps every period of 27 s */
-      idf %= BMF_NDF_PRD;
+    unsigned char *pkt = (unsigned char *)malloc((size_t)GSO_MAX * BMF_DF_SIZE);
+    const int G = gso < 1 ? 1 : (gso > GSO_MAX ? GSO_MAX : gso);
+    for (uint64_t f = 0; f < nframes && !failed; f += (uint64_t)G) {
+      const int ng = (nframes - f < (uint64_t)G) ? (int)(nframes - f) : G;
       for (int c = c_lo; c < c_hi; ++c) {
-        bmf_hdr_t h = {1, idf, sec, epoch, beam, freq0 + 7.0 * c};
-        bmf_hdr_encode(pkt, &h);
-        memcpy(pkt + BMF_HDR_SIZE, pool + ((f % ncache) * (uint64_t)nchunk + (uint64_t)c) * BMF_DT_SIZE, BMF_DT_SIZE);
-        const uint64_t counter = f * (uint64_t)nchunk + (uint64_t)c + 1;
-        if (drop_every > 0 && counter % (uint64_t)drop_every == 0) {
-          ++dropped;
-          continue;
+        int npk = 0; /* packets of chunk c, frames f .. f+ng-1, back to back in pkt */
+        for (int k = 0; k < ng; ++k) {
+          const uint64_t fk = f + (uint64_t)k;
+          uint64_t idf = idf0 + fk, sec = sec0;
+          sec += (idf / BMF_NDF_PRD) * BMF_PRD_SEC; /* the frame counter wraps every period of 27 s */
+          idf %= BMF_NDF_PRD;
+          const uint64_t counter = fk * (uint64_t)nchunk + (uint64_t)c + 1;
+          if (drop_every > 0 && counter % (uint64_t)drop_every == 0) {
+            ++dropped;
+            continue;
+          }
+          unsigned char *q = pkt + (size_t)npk * BMF_DF_SIZE;
+          bmf_hdr_t h = {1, idf, sec, epoch, beam, freq0 + 7.0 * c};
+          bmf_hdr_encode(q, &h);
+          memcpy(q + BMF_HDR_SIZE, pool + ((fk % ncache) * (uint64_t)nchunk + (uint64_t)c) * BMF_DT_SIZE, BMF_DT_SIZE);
+          ++npk;
         }
-        while (sendto(socks[c], pkt, BMF_DF_SIZE, 0, (struct sockaddr *)&dst[c], sizeof(dst[c])) < 0) {
+        if (!npk) continue;
+        struct iovec iov = {pkt, (size_t)npk * BMF_DF_SIZE};
+        struct msghdr mh;
+        char ctl[CMSG_SPACE(sizeof(uint16_t))];
+        memset(&mh, 0, sizeof(mh));
+        mh.msg_name = &dst[c];
+        mh.msg_namelen = sizeof(dst[c]);
+        mh.msg_iov = &iov;
+        mh.msg_iovlen = 1;
+        if (npk > 1) { /* one datagram train: the kernel cuts it every BMF_DF_SIZE bytes */
+          memset(ctl, 0, sizeof(ctl));
+          mh.msg_control = ctl;
+          mh.msg_controllen = sizeof(ctl);
+          struct cmsghdr *cm = CMSG_FIRSTHDR(&mh);
+          cm->cmsg_level = SOL_UDP;
+          cm->cmsg_type = UDP_SEGMENT;
+          cm->cmsg_len = CMSG_LEN(sizeof(uint16_t));
+          const uint16_t seg = BMF_DF_SIZE;
+          memcpy(CMSG_DATA(cm), &seg, sizeof(seg));
+        }
+        while (sendmsg(socks[c], &mh, 0) < 0) {
           if (errno == ENOBUFS || errno == EAGAIN || errno == EINTR) {
             usleep(20);
             continue;
           }
-          fprintf(stderr, "bmf_replay: sendto: %s\n", strerror(errno));
+          fprintf(stderr, "bmf_replay: sendmsg: %s\n", strerror(errno));
           failed = 1;
           break;
         }
-        ++sent;
+        sent += (uint64_t)npk;
       }
       if (rate > 0) { /* pace on absolute time so the average rate holds */
-        const double due = t0 + (double)(f + 1) / rate;
+        const double due = t0 + (double)(f + (uint64_t)ng) / rate;
         double dt = due - now_s();
         if (dt > 0) {
           struct timespec ts = {(time_t)dt, (long)((dt - (double)(time_t)dt) * 1e9)};

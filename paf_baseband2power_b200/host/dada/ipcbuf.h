@@ -78,7 +78,9 @@ char *ipcbuf_get_next_write(ipcbuf_t *id);
    ipcbuf_get_next_write); waits until the reader has freed it.  Lets the capture stage keep
    two blocks open so late packets of block k and early ones of k+1 both land in the ring
    (the reference spills into a malloc'ed side buffer and copies, capture.c:527-533). */
+#ifndef B2P_NO_SHIM_EXTENSIONS /* define to compile a client as against a stock PSRDADA */
 char *ipcbuf_get_write_ahead(ipcbuf_t *id, unsigned ahead);
+#endif
 int ipcbuf_mark_filled(ipcbuf_t *id, uint64_t nbytes);
 char *ipcbuf_get_next_read(ipcbuf_t *id, uint64_t *bytes);
 int ipcbuf_mark_cleared(ipcbuf_t *id);

@@ -20,22 +20,25 @@
 
 multilog_t *runtime_log;
 
+/* the first eight lines are the reference's usage text as it stands (paf_baseband2power.cu:17-28,
+   its spelling included): operators and wrapper scripts know it */
 static const char *const kUsage[] = {
-    "paf_baseband2power - To detect baseband data with original channels and integrate the detected data in time",
+    "paf_baseband2power - To detect baseband data with original channels and average the detected data in time",
     "",
-    "Usage: paf_baseband2power [options]",
-    " -a  Hexadecimal shared memory key for incoming ring buffer",
-    " -b  Hexadecimal shared memory key for outcoming ring buffer",
+    "Usage: paf_process [options]",
+    " -a  Hexacdecimal shared memory key for incoming ring buffer",
+    " -b  Hexacdecimal shared memory key for outcoming ring buffer",
     " -c  The name of the directory in which we will record the data",
-    " -d  The index of GPU (extension: a list 0,1,2,3 spreads the beam's channel groups over the GPUs)",
+    " -d  The index of GPU",
     " -h  show help",
     "extensions:",
+    " -d  may be a list (0,1,2,3): the beam's channel groups are spread over those GPUs",
+    " -g  chunks per GPU for a -d list, e.g. 5,5,7,7 (default: in proportion to the host-link rates)",
     " -s  0 integral over the integration (default), 1 average in time",
     " -n  data frames per integration (default: frames of one input block)",
     " -k  kernel: auto | ldg | tma",
     " -e  1 big-endian samples (default), 0 little-endian",
     " -p  1 page-lock the input ring (default), 0 leave it pageable",
-    " -g  chunks per GPU for a -d list, e.g. 5,5,7,7 (default: in proportion to the host-link rates)",
     NULL};
 
 static int kernel_by_name(const char *name)
@@ -48,7 +51,7 @@ static int kernel_by_name(const char *name)
 /* returns 0 to go on, 1 to leave with EXIT_FAILURE (help or a bad option) */
 static int parse_args(int argc, char *argv[], conf_t *conf)
 {
-  for (int opt; (opt = getopt(argc, argv, "a:b:c:d:hs:n:k:e:p:g:")) != -1;) {
+  for (int opt; (opt = getopt(argc, argv, "a:b:c:d:h::s:n:k:e:p:g:")) != -1;) {
     if (opt == 'a' || opt == 'b') {
       if (cli_hex_key(optarg, opt == 'a' ? &conf->key_in : &conf->key_out, __FILE__, __LINE__)) return 1;
     } else if (opt == 'c') {

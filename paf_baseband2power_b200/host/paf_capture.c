@@ -12,14 +12,26 @@
  *
  * New design (the reference's is known to drop frames, capture.c:20-29, and
  * swaps its block pointer under running memcpys, sync.c:109 vs capture.c:542):
- * one thread per port pulling batches with recvmmsg; two ring blocks are open
- * at once (current and next), so packets that straddle a block boundary land
- * directly in the ring with no side buffer and no extra copy; a block is closed
- * under a write lock only once a packet two blocks ahead shows up; packets that
- * never arrived are zero-filled and counted, so a block never carries stale
- * data from its previous use.
+ * one thread per port pulling batches with recvmmsg — with UDP_GRO where the
+ * kernel offers it, so one message carries up to 8 frames of a source — and a
+ * window of the current ring block plus the start of the next one, so packets
+ * that straddle a block boundary are never dropped; the window moves on under
+ * a write lock; packets that never arrived are zero-filled and counted, so a
+ * block never carries stale data from its previous use.
  *
- * Extra flags: -I bind address, -p first port, -n ports, -t socket timeout [s].
+ * Two ring back-ends, chosen at compile time:
+ *   default              two ring blocks open at once (ipcbuf_get_write_ahead, an
+ *                        extension of this repo's ring shim): straddlers land in the
+ *                        ring directly, no side buffer, no copy.
+ *   -DB2P_STOCK_PSRDADA  only ipcio_open_block_write / ipcio_close_block_write — the
+ *                        two calls the reference's capture makes (capture.c:316,
+ *                        sync.c:101-109) — so it links against a stock -lpsrdada: one
+ *                        block open, the head of the next block kept in a small spill
+ *                        buffer (-w frames, default 256) and copied in when the block
+ *                        opens (the role of the reference's tbuf, sync.c:150-165).
+ *
+ * Extra flags: -I bind address, -p first port, -n ports, -t socket timeout [s],
+ * -w spill window in frames (stock back-end), -G 0 switches UDP_GRO off.
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -29,6 +41,7 @@
 #include <errno.h>
 #include <math.h>
 #include <netinet/in.h>
+#include <netinet/udp.h>
 #include <pthread.h>
 #include <stdatomic.h>
 #include <stdio.h>
@@ -46,8 +59,12 @@
 
 #define MSTR_LEN 512
 #define HN_LEN 8
-#define BATCH 32
+#define BATCH 16
 #define SECDAY 86400.0
+#ifndef UDP_GRO
+#define UDP_GRO 104
+#endif
+#define GRO_MAX 65536 /* largest coalesced datagram the kernel hands over */
 
 multilog_t *runtime_log;
 
@@ -60,8 +77,10 @@ typedef struct open_block_t {
 typedef struct capture_t {
   /* command line */
   key_t key;
-  int sod, keep_hdr, nic, nports, port_base, nchunk, timeout_s;
+  int sod, keep_hdr, nic, nports, port_base, nchunk, timeout_s, want_gro, gro_on;
   uint64_t ndf_block;
+  uint64_t ahead_ndf; /* frames of the next block the window covers: the whole block with the
+                         write-ahead back-end, the spill window with the stock one */
   double freq, length;
   char hfname[MSTR_LEN], efname[MSTR_LEN], dir[MSTR_LEN], ip[64];
   /* derived */
@@ -79,9 +98,10 @@ typedef struct capture_t {
   int64_t base; /* index of blk[0] */
   int header_done;
   /* statistics */
-  atomic_ullong n_recv, n_late, n_early, n_invalid, n_missing, n_blocks;
+  atomic_ullong n_recv, n_late, n_early, n_invalid, n_missing, n_blocks, n_msgs, ns_blocked;
   atomic_ullong port_recv[16];
-  atomic_int quit;
+  volatile int port_done[16]; /* the port has seen a frame past the requested length */
+  atomic_int quit, ndone;
 } capture_t;
 
 #define CAP_ERR(...)                                                                \
@@ -108,7 +128,8 @@ static void usage(void)
           " -j Length of the capture in seconds \n"
           " -k Directory for the log file \n"
           " -h Show help \n"
-          "extensions: -I bind address  -p first port [17100]  -n ports [6]  -t socket timeout s [27]\n");
+          "extensions: -I bind address  -p first port [17100]  -n ports [6]  -t socket timeout s [27]\n"
+          "            -w spill window in frames (stock PSRDADA back-end) [256]  -G 0 no UDP_GRO\n");
 }
 
 /* UTC_START / PICOSECONDS of the reference frame: capture.c:791-843 (acquire_start_time) */
@@ -173,17 +194,100 @@ static int register_header(capture_t *c)
   return 0;
 }
 
-static void open_slot(capture_t *c, int slot, int64_t index)
+static void stop_all(capture_t *c);
+
+static uint64_t now_ns(void)
 {
-  ipcbuf_t *db = (ipcbuf_t *)c->hdu->data_block;
-  c->blk[slot].buf = ipcbuf_get_write_ahead(db, (unsigned)slot);
-  c->blk[slot].index = index;
-  memset(c->blk[slot].seen, 0, c->ndf_block * (uint64_t)c->nchunk);
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
 }
 
-/* Close blk[0] (zero-fill what never arrived), slide blk[1] down, open a new blk[1].
-   Caller holds the write lock. */
-static void rotate(capture_t *c)
+#ifdef B2P_STOCK_PSRDADA
+/* ---- stock PSRDADA: one open ring block + a spill buffer for the head of the next ---- */
+static int open_first(capture_t *c)
+{
+  uint64_t id = 0;
+  c->blk[0].buf = ipcio_open_block_write(c->hdu->data_block, &id); /* capture.c:316 */
+  c->blk[1].buf = (char *)malloc(c->ahead_ndf * (uint64_t)c->nchunk * (uint64_t)c->pkt_size);
+  if (!c->blk[0].buf || !c->blk[1].buf) return -1;
+  c->blk[0].index = 0;
+  c->blk[1].index = 1;
+  memset(c->blk[0].seen, 0, c->ndf_block * (uint64_t)c->nchunk);
+  memset(c->blk[1].seen, 0, c->ndf_block * (uint64_t)c->nchunk);
+  return 0;
+}
+
+/* close the current block and (open_next) open the next one; what the spill buffer caught moves in */
+static int advance(capture_t *c, int open_next)
+{
+  const uint64_t t0 = now_ns();
+  if (ipcio_close_block_write(c->hdu->data_block, c->rbufsz) < 0) return -1; /* sync.c:101 */
+  if (!open_next) {
+    c->blk[0].buf = NULL;
+    return 0;
+  }
+  uint64_t id = 0;
+  char *next = ipcio_open_block_write(c->hdu->data_block, &id);               /* sync.c:109 */
+  atomic_fetch_add(&c->ns_blocked, now_ns() - t0);
+  if (!next) return -1;
+  const uint64_t nspill = c->ahead_ndf * (uint64_t)c->nchunk;
+  for (uint64_t i = 0; i < nspill; ++i)
+    if (c->blk[1].seen[i])
+      memcpy(next + i * (uint64_t)c->pkt_size, c->blk[1].buf + i * (uint64_t)c->pkt_size, (size_t)c->pkt_size);
+  unsigned char *seen0 = c->blk[0].seen;
+  c->blk[0].seen = c->blk[1].seen; /* the spill's marks are the new block's marks */
+  c->blk[0].buf = next;
+  c->blk[1].seen = seen0;
+  memset(c->blk[1].seen, 0, c->ndf_block * (uint64_t)c->nchunk);
+  return 0;
+}
+#else
+/* ---- ring shim: the next block is open in the ring as well (ipcbuf_get_write_ahead) ---- */
+static int open_slot(capture_t *c, int slot, int64_t index)
+{
+  ipcbuf_t *db = (ipcbuf_t *)c->hdu->data_block;
+  const uint64_t t0 = now_ns();
+  c->blk[slot].buf = ipcbuf_get_write_ahead(db, (unsigned)slot); /* waits while the ring is full */
+  atomic_fetch_add(&c->ns_blocked, now_ns() - t0);
+  c->blk[slot].index = index;
+  memset(c->blk[slot].seen, 0, c->ndf_block * (uint64_t)c->nchunk);
+  return c->blk[slot].buf ? 0 : -1; /* NULL: the ring was destroyed under us */
+}
+
+static int open_first(capture_t *c)
+{
+  if (open_slot(c, 0, 0) < 0) return -1;
+  return open_slot(c, 1, 1);
+}
+
+static int advance(capture_t *c, int open_next)
+{
+  if (ipcbuf_mark_filled((ipcbuf_t *)c->hdu->data_block, c->rbufsz) < 0) return -1;
+  unsigned char *seen0 = c->blk[0].seen;
+  c->blk[0] = c->blk[1]; /* after mark_filled, "ahead 1" has become "ahead 0" */
+  c->blk[1].seen = seen0;
+  if (!open_next) { /* end of the capture: nothing will be written beyond blk[0] */
+    c->blk[1].buf = NULL;
+    memset(c->blk[1].seen, 0, c->ndf_block * (uint64_t)c->nchunk);
+    return 0;
+  }
+  return open_slot(c, 1, c->base + 2);
+}
+#endif
+
+static int any_seen(const capture_t *c, int slot)
+{
+  const uint64_t n = (slot ? c->ahead_ndf : c->ndf_block) * (uint64_t)c->nchunk;
+  for (uint64_t i = 0; i < n; ++i)
+    if (c->blk[slot].seen[i]) return 1;
+  return 0;
+}
+
+/* Retire blk[0] (zero-fill what never arrived) and move the window one block on.
+   Caller holds the write lock.  A ring that can not deliver the next block (destroyed, or an
+   error from the ring library) ends the capture instead of writing through a NULL pointer. */
+static void rotate(capture_t *c, int open_next)
 {
   open_block_t *b = &c->blk[0];
   const uint64_t npkt = c->ndf_block * (uint64_t)c->nchunk;
@@ -194,13 +298,13 @@ static void rotate(capture_t *c)
       ++missing;
     }
   atomic_fetch_add(&c->n_missing, missing);
-  ipcbuf_mark_filled((ipcbuf_t *)c->hdu->data_block, c->rbufsz);
   atomic_fetch_add(&c->n_blocks, 1);
-  unsigned char *seen0 = c->blk[0].seen;
-  c->blk[0] = c->blk[1]; /* after mark_filled, "ahead 1" has become "ahead 0" */
-  c->blk[1].seen = seen0;
+  if (advance(c, open_next) < 0) {
+    CAP_ERR("The ring gave no next block (destroyed?), stopping\n");
+    c->blk[0].buf = c->blk[1].buf = NULL;
+    stop_all(c);
+  }
   c->base += 1;
-  open_slot(c, 1, c->base + 1);
 }
 
 /* Stop every port thread now: a blocked recvmmsg returns once its socket is shut down. */
@@ -215,25 +319,97 @@ typedef struct port_arg_t {
   int iport;
 } port_arg_t;
 
+/* one BMF frame (header + payload) from source address `from` into the window; the caller
+   holds the read lock and gets it back */
+static void place_frame(capture_t *c, int iport, const unsigned char *frame, const struct sockaddr_in *from)
+{
+  bmf_hdr_t h;
+  bmf_hdr_decode(frame, &h);
+  const unsigned char *ip = (const unsigned char *)&from->sin_addr.s_addr;
+  const int ifreq = bmf_chunk_of_source(ip[2], ip[3]);
+  if (ifreq < 0 || ifreq >= c->nchunk) {
+    atomic_fetch_add(&c->n_invalid, 1);
+    return;
+  }
+  if (!c->have_ref) { /* first frame of the stream: it becomes frame 0 */
+    pthread_rwlock_unlock(&c->win);
+    pthread_rwlock_wrlock(&c->win);
+    if (!c->have_ref) {
+      c->ref = h;
+      c->have_ref = 1;
+      c->base = 0;
+      if (register_header(c) < 0 || open_first(c) < 0) {
+        c->blk[0].buf = c->blk[1].buf = NULL;
+        stop_all(c);
+      }
+    }
+    pthread_rwlock_unlock(&c->win);
+    pthread_rwlock_rdlock(&c->win);
+  }
+  const int64_t f = bmf_frames_since(h.sec, h.idf, c->ref.sec, c->ref.idf);
+  if (f < 0) {
+    atomic_fetch_add(&c->n_early, 1);
+    return;
+  }
+  if (f >= c->nframes_total) { /* the requested length is in on this port */
+    c->port_done[iport] = 1;
+    return;
+  }
+  const int64_t bi = f / (int64_t)c->ndf_block;
+  const uint64_t fin = (uint64_t)(f % (int64_t)c->ndf_block);
+  /* beyond the window (two blocks ahead, or past the spill window of the next block):
+     retire the oldest block */
+  while ((bi > c->base + 1 || (bi == c->base + 1 && fin >= c->ahead_ndf)) && !atomic_load(&c->quit)) {
+    pthread_rwlock_unlock(&c->win);
+    pthread_rwlock_wrlock(&c->win);
+    if (bi > c->base + 1 || (bi == c->base + 1 && fin >= c->ahead_ndf)) rotate(c, 1);
+    pthread_rwlock_unlock(&c->win);
+    pthread_rwlock_rdlock(&c->win);
+  }
+  if (bi < c->base) {
+    atomic_fetch_add(&c->n_late, 1);
+    return;
+  }
+  if (bi > c->base + 1 || (bi == c->base + 1 && fin >= c->ahead_ndf)) return; /* quitting */
+  open_block_t *b = &c->blk[bi - c->base];
+  if (!b->buf) return; /* the ring went away */
+  const uint64_t slot = fin * (uint64_t)c->nchunk + (uint64_t)ifreq;
+  memcpy(b->buf + slot * (uint64_t)c->pkt_size, frame + c->pkt_offset, (size_t)c->pkt_size);
+  b->seen[slot] = 1;
+  atomic_fetch_add(&c->n_recv, 1);
+  atomic_fetch_add(&c->port_recv[iport], 1);
+}
+
 static void *port_thread(void *argp)
 {
   port_arg_t *pa = (port_arg_t *)argp;
   capture_t *c = pa->c;
   const int sock = c->socks[pa->iport];
-  static __thread unsigned char frames[BATCH][BMF_DF_SIZE];
+  /* with UDP_GRO one message is up to GRO_MAX bytes: several frames of one source, back to back */
+  const size_t cap = c->gro_on ? GRO_MAX : BMF_DF_SIZE;
+  unsigned char *frames = (unsigned char *)malloc((size_t)BATCH * cap);
   struct mmsghdr msgs[BATCH];
   struct iovec iov[BATCH];
   struct sockaddr_in from[BATCH];
+  char ctl[BATCH][CMSG_SPACE(sizeof(int)) + 32];
+  if (!frames) {
+    stop_all(c);
+    return NULL;
+  }
 
   while (!atomic_load(&c->quit)) {
     for (int i = 0; i < BATCH; ++i) {
-      iov[i].iov_base = frames[i];
-      iov[i].iov_len = BMF_DF_SIZE;
+      iov[i].iov_base = frames + (size_t)i * cap;
+      iov[i].iov_len = cap;
       memset(&msgs[i], 0, sizeof(msgs[i]));
       msgs[i].msg_hdr.msg_iov = &iov[i];
       msgs[i].msg_hdr.msg_iovlen = 1;
       msgs[i].msg_hdr.msg_name = &from[i];
       msgs[i].msg_hdr.msg_namelen = sizeof(from[i]);
+      if (c->gro_on) {
+        msgs[i].msg_hdr.msg_control = ctl[i];
+        msgs[i].msg_hdr.msg_controllen = sizeof(ctl[i]);
+      }
     }
     const int n = recvmmsg(sock, msgs, BATCH, MSG_WAITFORONE, NULL);
     if (n <= 0) {
@@ -244,65 +420,37 @@ static void *port_thread(void *argp)
       stop_all(c);
       break;
     }
+    atomic_fetch_add(&c->n_msgs, (unsigned long long)n);
     pthread_rwlock_rdlock(&c->win);
     for (int i = 0; i < n; ++i) {
-      if (msgs[i].msg_len != BMF_DF_SIZE) {
+      const unsigned char *m = frames + (size_t)i * cap;
+      size_t len = msgs[i].msg_len, seg = len;
+      if (c->gro_on) /* the segment size of a coalesced message comes as a control message */
+        for (struct cmsghdr *cm = CMSG_FIRSTHDR(&msgs[i].msg_hdr); cm; cm = CMSG_NXTHDR(&msgs[i].msg_hdr, cm))
+          if (cm->cmsg_level == SOL_UDP && cm->cmsg_type == UDP_GRO) {
+            int v = 0;
+            memcpy(&v, CMSG_DATA(cm), sizeof(v));
+            if (v > 0) seg = (size_t)v;
+          }
+      if (seg != BMF_DF_SIZE || len % BMF_DF_SIZE) {
         if (!atomic_load(&c->quit)) atomic_fetch_add(&c->n_invalid, 1);
         continue;
       }
-      bmf_hdr_t h;
-      bmf_hdr_decode(frames[i], &h);
-      const unsigned char *ip = (const unsigned char *)&from[i].sin_addr.s_addr;
-      const int ifreq = bmf_chunk_of_source(ip[2], ip[3]);
-      if (ifreq < 0 || ifreq >= c->nchunk) {
-        atomic_fetch_add(&c->n_invalid, 1);
-        continue;
-      }
-      if (!c->have_ref) { /* first frame of the stream: it becomes frame 0 */
-        pthread_rwlock_unlock(&c->win);
-        pthread_rwlock_wrlock(&c->win);
-        if (!c->have_ref) {
-          c->ref = h;
-          c->have_ref = 1;
-          if (register_header(c) < 0) stop_all(c);
-          open_slot(c, 0, 0);
-          open_slot(c, 1, 1);
-          c->base = 0;
-        }
-        pthread_rwlock_unlock(&c->win);
-        pthread_rwlock_rdlock(&c->win);
-      }
-      const int64_t f = bmf_frames_since(h.sec, h.idf, c->ref.sec, c->ref.idf);
-      if (f < 0) {
-        atomic_fetch_add(&c->n_early, 1);
-        continue;
-      }
-      if (f >= c->nframes_total) { /* the requested length is in */
-        stop_all(c);
-        continue;
-      }
-      int64_t bi = f / (int64_t)c->ndf_block;
-      while (bi > c->base + 1 && !atomic_load(&c->quit)) { /* two blocks ahead: retire the oldest */
-        pthread_rwlock_unlock(&c->win);
-        pthread_rwlock_wrlock(&c->win);
-        if (bi > c->base + 1) rotate(c);
-        pthread_rwlock_unlock(&c->win);
-        pthread_rwlock_rdlock(&c->win);
-      }
-      if (bi < c->base) {
-        atomic_fetch_add(&c->n_late, 1);
-        continue;
-      }
-      if (bi > c->base + 1) continue; /* quitting */
-      open_block_t *b = &c->blk[bi - c->base];
-      const uint64_t slot = (uint64_t)(f % (int64_t)c->ndf_block) * (uint64_t)c->nchunk + (uint64_t)ifreq;
-      memcpy(b->buf + slot * (uint64_t)c->pkt_size, frames[i] + c->pkt_offset, (size_t)c->pkt_size);
-      b->seen[slot] = 1;
-      atomic_fetch_add(&c->n_recv, 1);
-      atomic_fetch_add(&c->port_recv[pa->iport], 1);
+      for (size_t off = 0; off < len; off += BMF_DF_SIZE) place_frame(c, pa->iport, m + off, &from[i]);
     }
     pthread_rwlock_unlock(&c->win);
+    if (c->port_done[pa->iport]) {
+      /* This port is through.  The others may still have frames of the last block queued in
+         their socket buffers: the first port to finish gives them up to 2 s to get there
+         before everything is stopped (a port whose last packets were lost never would). */
+      if (atomic_fetch_add(&c->ndone, 1) == 0) {
+        for (int k = 0; k < 200 && atomic_load(&c->ndone) < c->nports && !atomic_load(&c->quit); ++k) usleep(10000);
+        stop_all(c);
+      }
+      break;
+    }
   }
+  free(frames);
   return NULL;
 }
 
@@ -313,9 +461,20 @@ static int init_sockets(capture_t *c)
     if (s < 0) return -1;
     int one = 1, rcv = 256 << 20;
     setsockopt(s, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
-    setsockopt(s, SOL_SOCKET, SO_RCVBUF, &rcv, sizeof(rcv));
+    /* a deep socket buffer rides out scheduling hiccups; root may go past net.core.rmem_max */
+    if (setsockopt(s, SOL_SOCKET, SO_RCVBUFFORCE, &rcv, sizeof(rcv)) < 0)
+      setsockopt(s, SOL_SOCKET, SO_RCVBUF, &rcv, sizeof(rcv));
     struct timeval tv = {c->timeout_s, 0}; /* SO_RCVTIMEO, capture.c:149,158 */
     setsockopt(s, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    if (c->want_gro && i == 0) c->gro_on = 1;
+    if (c->gro_on && setsockopt(s, IPPROTO_UDP, UDP_GRO, &one, sizeof(one)) < 0) {
+      if (i == 0)
+        c->gro_on = 0; /* kernel without UDP_GRO: plain datagrams */
+      else {
+        CAP_ERR("UDP_GRO accepted on the first port only (%s)\n", strerror(errno));
+        return -1;
+      }
+    }
     struct sockaddr_in sa;
     memset(&sa, 0, sizeof(sa));
     sa.sin_family = AF_INET;
@@ -341,9 +500,11 @@ int main(int argc, char **argv)
   c->port_base = BMF_PORT_BASE;
   c->nchunk = BMF_NCHK_NIC;
   c->timeout_s = BMF_PRD_SEC;
+  c->want_gro = 1;
+  c->ahead_ndf = 256;
   strcpy(c->dir, ".");
   int arg;
-  while ((arg = getopt(argc, argv, "a:b:c:d:e:f:g:hi:j:k:I:p:n:t:")) != -1) {
+  while ((arg = getopt(argc, argv, "a:b:c:d:e:f:g:hi:j:k:I:p:n:t:w:G:")) != -1) {
     switch (arg) {
       case 'h': usage(); return EXIT_FAILURE;
       case 'a':
@@ -365,6 +526,8 @@ int main(int argc, char **argv)
       case 'p': c->port_base = atoi(optarg); break;
       case 'n': c->nports = atoi(optarg); break;
       case 't': c->timeout_s = atoi(optarg); break;
+      case 'w': c->ahead_ndf = strtoull(optarg, NULL, 10); break;
+      case 'G': c->want_gro = atoi(optarg) != 0; break;
       default: usage(); return EXIT_FAILURE;
     }
   }
@@ -396,6 +559,12 @@ int main(int argc, char **argv)
   c->pkt_offset = c->keep_hdr ? 0 : BMF_HDR_SIZE;
   c->rbufsz = c->ndf_block * (uint64_t)c->nchunk * (uint64_t)c->pkt_size;
   c->nframes_total = (int64_t)ceil(c->length / BMF_TDF_SEC - 1e-9);
+#ifdef B2P_STOCK_PSRDADA
+  if (c->ahead_ndf < 1) c->ahead_ndf = 1;
+  if (c->ahead_ndf > c->ndf_block) c->ahead_ndf = c->ndf_block;
+#else
+  c->ahead_ndf = c->ndf_block; /* the whole next block is open in the ring */
+#endif
   pthread_rwlock_init(&c->win, NULL);
   for (int s = 0; s < 2; ++s) {
     c->blk[s].seen = (unsigned char *)malloc(c->ndf_block * (uint64_t)c->nchunk);
@@ -414,10 +583,12 @@ int main(int argc, char **argv)
     CAP_ERR("Buffer size mismatch: ring block %lu, expected %lu\n", (unsigned long)ipcbuf_get_bufsz(db), (unsigned long)c->rbufsz);
     return EXIT_FAILURE;
   }
+#ifndef B2P_STOCK_PSRDADA
   if (ipcbuf_get_nbufs(db) < 3) {
     CAP_ERR("The ring needs at least 3 blocks (two are open at once)\n");
     return EXIT_FAILURE;
   }
+#endif
   if (dada_hdu_lock_write(c->hdu) < 0) {
     CAP_ERR("Error locking HDU\n");
     return EXIT_FAILURE;
@@ -441,13 +612,15 @@ int main(int argc, char **argv)
   clock_gettime(CLOCK_MONOTONIC, &t1);
 
   /* flush: a block that received anything is delivered whole (zero-filled), an untouched one is not */
-  if (c->have_ref) {
-    const uint64_t npkt = c->ndf_block * (uint64_t)c->nchunk;
-    for (int s = 0; s < 2; ++s) {
-      int any = 0;
-      for (uint64_t i = 0; i < npkt && !any; ++i) any = c->blk[0].seen[i];
-      if (!any) break;
-      rotate(c);
+  if (c->have_ref && c->blk[0].buf) {
+    if (any_seen(c, 0) || any_seen(c, 1)) {
+      const int more = any_seen(c, 1);
+      rotate(c, more);                                 /* the current block */
+      if (more && c->blk[0].buf) rotate(c, 0);         /* and the one that had been started */
+    } else {
+#ifdef B2P_STOCK_PSRDADA
+      ipcio_close_block_write(c->hdu->data_block, 0);  /* opened, never written: hand it back empty */
+#endif
     }
   }
 
@@ -459,6 +632,10 @@ int main(int argc, char **argv)
            (unsigned long long)atomic_load(&c->n_missing), (unsigned long long)atomic_load(&c->n_late),
            (unsigned long long)atomic_load(&c->n_early), (unsigned long long)atomic_load(&c->n_invalid),
            (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+  multilog(runtime_log, LOG_INFO, "udp_gro %s  messages %llu (%.2f frames per message)  blocked on a full ring %.3f s\n",
+           c->gro_on ? "on" : "off", (unsigned long long)atomic_load(&c->n_msgs),
+           (double)atomic_load(&c->n_recv) / (double)(atomic_load(&c->n_msgs) ? atomic_load(&c->n_msgs) : 1),
+           1e-9 * (double)atomic_load(&c->ns_blocked));
   for (int i = 0; i < c->nports; ++i)
     multilog(runtime_log, LOG_INFO, "port %d: %llu frames\n", c->port_base + i, (unsigned long long)atomic_load(&c->port_recv[i]));
 

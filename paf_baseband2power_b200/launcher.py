@@ -26,7 +26,7 @@ import threading
 from dataclasses import dataclass, field
 from typing import List
 
-from .sharding import ring_keys_for_beam
+from .sharding import gpu_for_rank, ring_keys_for_beam
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(PKG, "bin")
@@ -97,8 +97,10 @@ def _pin(cmd: List[str], cpu: int | None) -> List[str]:
 
 
 def plan(conf: PipelineConf, directory: str, dfnames: List[str], gpus: List[int], memcheck: bool = False,
-         hfname: str | None = None, extra_stage_args: List[str] | None = None, pin: bool = True) -> List[BeamPlan]:
-    """The exact commands for every beam; nothing is executed here."""
+         hfname: str | None = None, extra_stage_args: List[str] | None = None, pin: bool = True,
+         ngpus_box: int = 0) -> List[BeamPlan]:
+    """The exact commands for every beam; nothing is executed here.  `gpus` empty: beams are
+    spread over the `ngpus_box` GPUs of the box (sharding.gpu_for_rank)."""
     plans = []
     hf = hfname or conf.diskdb_hfname
     if not os.path.isabs(hf):
@@ -109,7 +111,7 @@ def plan(conf: PipelineConf, directory: str, dfnames: List[str], gpus: List[int]
             kin, kout = conf.diskdb_key, conf.b2p_key
         else:
             kin, kout = ring_keys_for_beam(beam, conf.diskdb_key, conf.b2p_key)
-        gpu = gpus[beam % len(gpus)]
+        gpu = gpus[beam % len(gpus)] if gpus else gpu_for_rank(beam, len(dfnames), ngpus_box, "spread")
         bp = BeamPlan(beam, gpu, kin, kout)
         db = os.path.join(BIN, "paf_dada_db")
         bp.create = [
@@ -141,35 +143,54 @@ def write_key_files(conf: PipelineConf, directory: str, plans: List[BeamPlan]):
                 f.write(f"key {key:x}\n")
 
 
-def run(plans: List[BeamPlan], timeout: float | None = None) -> int:
-    """Create rings, run the three stages of every beam concurrently, destroy rings."""
+def run(plans: List[BeamPlan], timeout: float | None = None, poll_s: float = 0.2) -> int:
+    """Create rings, run the three stages of every beam concurrently, destroy rings.
+
+    A stage that dies (no GPU, size mismatch, ...) would leave its siblings blocked on a ring
+    for ever — the producer in ipcbuf_get_next_write, the writer waiting for a header.  So the
+    processes are watched together: the first non-zero exit (or the timeout) terminates what
+    is still running of that beam's pipeline, and the rings are destroyed in any case."""
+    import time
     rc = 0
     created: List[BeamPlan] = []
+    procs: List[tuple] = []          # (beam index, Popen)
     try:
         for bp in plans:
             for cmd in bp.create:
                 subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
             created.append(bp)
-        procs, results = [], {}
-
-        def wait(i, p):
-            try:
-                results[i] = p.wait(timeout=timeout)
-            except subprocess.TimeoutExpired:
-                p.kill()
-                results[i] = -9
-
-        for bp in plans:
+        for bi, bp in enumerate(plans):
             # consumer first, producer last: nobody blocks on a ring without a reader
             for cmd in (bp.stages[2], bp.stages[1], bp.stages[0]):
-                procs.append(subprocess.Popen(cmd))
-        threads = [threading.Thread(target=wait, args=(i, p)) for i, p in enumerate(procs)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        rc = max((abs(v) for v in results.values()), default=0)
+                procs.append((bi, subprocess.Popen(cmd)))
+        deadline = None if timeout is None else time.monotonic() + timeout
+        failed_beams = set()
+        while any(p.poll() is None for _, p in procs):
+            for bi, p in procs:
+                code = p.poll()
+                if code not in (None, 0) and bi not in failed_beams:
+                    failed_beams.add(bi)
+                    for bj, q in procs:          # its siblings can only hang now
+                        if bj == bi and q.poll() is None:
+                            q.terminate()
+            if deadline is not None and time.monotonic() > deadline:
+                for _, p in procs:
+                    if p.poll() is None:
+                        p.kill()
+                rc = max(rc, 9)
+                break
+            time.sleep(poll_s)
+        for _, p in procs:
+            try:
+                code = p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                code = p.wait()
+            rc = max(rc, abs(code))
     finally:
+        for _, p in procs:
+            if p.poll() is None:
+                p.kill()
         for bp in created:
             for cmd in bp.destroy:
                 subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -187,6 +208,9 @@ def main(argv=None) -> int:
     ap.add_argument("--ndf", type=int, default=0, help="override NDF (frames per ring block) of the conf")
     ap.add_argument("--nblk", type=int, default=0, help="override NBLK (input ring blocks) of the conf")
     ap.add_argument("--average", type=int, default=0, help="1: time average instead of integral")
+    ap.add_argument("--spread", type=int, default=0, metavar="NGPU",
+                    help="ignore -c and spread the beams over the box's NGPU GPUs (beam i -> GPU floor(i*NGPU/nbeams)): "
+                         "neighbouring GPUs tend to share a host bridge, and this path is bound by the host links")
     ap.add_argument("--dry-run", action="store_true", help="print the commands, run nothing")
     ap.add_argument("--timeout", type=float, default=None)
     args = ap.parse_args(argv)
@@ -199,7 +223,8 @@ def main(argv=None) -> int:
     if args.visiblegpu not in ("", "all"):
         os.environ["CUDA_VISIBLE_DEVICES"] = args.visiblegpu
     extra = ["-s", "1"] if args.average else []
-    plans = plan(conf, args.directory, args.dfname, args.gpu, bool(args.memcheck), extra_stage_args=extra)
+    plans = plan(conf, args.directory, args.dfname, [] if args.spread else args.gpu, bool(args.memcheck),
+                 extra_stage_args=extra, ngpus_box=args.spread)
     if args.dry_run:
         for bp in plans:
             for cmd in bp.create + bp.stages + bp.destroy:

@@ -63,7 +63,19 @@ def test_header_decode_matches_reference_hdr_c(tmp_path):
     assert [lib.chunk(1, 1), lib.chunk(1, 2), lib.chunk(1, 11), lib.chunk(2, 1), lib.chunk(8, 12)] == [0, 0, 5, 6, 47]
 
 
-def _capture_run(tmp_path, ndf_block, nframes_capture, nframes_sent, seed, drop_every=0, rate=800):
+# (capture binary, extra capture flags, extra replay flags): the ring-shim back-end with two open
+# blocks and the stock-PSRDADA back-end (open/close_block_write + spill window), each with plain
+# datagrams and with UDP segmentation offload on the sender / UDP_GRO on the receiver
+VARIANTS = {
+    "ahead-gro": ("paf_capture", [], ["-G", "8"]),
+    "ahead-plain": ("paf_capture", ["-G", "0"], []),
+    "stock-gro": ("paf_capture_stock", ["-w", "4"], ["-G", "5"]),
+    "stock-plain": ("paf_capture_stock", ["-G", "0", "-w", "2"], []),
+}
+
+
+def _capture_run(tmp_path, ndf_block, nframes_capture, nframes_sent, seed, drop_every=0, rate=800, variant="ahead-plain"):
+    exe, cap_extra, rep_extra = VARIANTS[variant]
     key = "%x" % (random.randint(0x2000, 0xDFFF) & 0xFFF0)
     port = random.randint(20000, 40000)
     run = lambda *c: subprocess.run(list(c), check=True, capture_output=True, text=True, timeout=120)
@@ -71,12 +83,12 @@ def _capture_run(tmp_path, ndf_block, nframes_capture, nframes_sent, seed, drop_
     try:
         sink = subprocess.Popen([os.path.join(BIN, "paf_dbdisk"), "-k", key, "-D", str(tmp_path), "-f", "cap.dada", "-W"],
                                 stderr=subprocess.PIPE)
-        cap = subprocess.Popen([os.path.join(BIN, "paf_capture"), "-a", key, "-b", "1", "-c", str(ndf_block), "-d", "0",
+        cap = subprocess.Popen([os.path.join(BIN, exe), "-a", key, "-b", "1", "-c", str(ndf_block), "-d", "0",
                                 "-f", HDR, "-g", "none", "-i", "1340.5", "-j", repr(nframes_capture * 1.08e-4),
-                                "-k", str(tmp_path), "-I", "127.0.0.1", "-p", str(port), "-t", "3"], stderr=subprocess.PIPE)
+                                "-k", str(tmp_path), "-I", "127.0.0.1", "-p", str(port), "-t", "3"] + cap_extra, stderr=subprocess.PIPE)
         time.sleep(0.5)
         args = [os.path.join(BIN, "bmf_replay"), "-D", "127.0.0.1", "-p", str(port), "-n", str(nframes_sent),
-                "-s", str(seed), "-r", str(rate), "-i", "249990"]      # the frame counter wraps mid-run
+                "-s", str(seed), "-r", str(rate), "-i", "249990"] + rep_extra      # the frame counter wraps mid-run
         if drop_every:
             args += ["-L", str(drop_every)]
         rep = run(*args)
@@ -89,12 +101,13 @@ def _capture_run(tmp_path, ndf_block, nframes_capture, nframes_sent, seed, drop_
     return data, log, rep.stdout
 
 
-def test_capture_assembles_the_generator_block(tmp_path, oracle_mod):
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_capture_assembles_the_generator_block(tmp_path, oracle_mod, variant):
     """40 frames captured into 16-frame blocks: every packet that arrived sits at
     (idf*48 + chunk)*7168 (capture.c:540-542) and equals the generator; what did not arrive
     (UDP may drop, and the tail of the last block was never sent) is zero and is counted."""
     ndf_block, ncap, nsent = 16, 40, 44
-    data, log, _ = _capture_run(tmp_path, ndf_block, ncap, nsent, seed=9)
+    data, log, _ = _capture_run(tmp_path, ndf_block, ncap, nsent, seed=9, variant=variant)
     nblk = (ncap + ndf_block - 1) // ndf_block
     assert data.size == 4096 + nblk * ndf_block * FRAME
     pay = data[4096:]
@@ -118,11 +131,37 @@ def test_capture_assembles_the_generator_block(tmp_path, oracle_mod):
     kv = hdr_kv(hdr)
     assert kv["UTC_START"] == "2018-07-02-10:30:26" and kv["FREQ"] == "1340.5"   # 27000 s + 249990*108us
     assert kv["PICOSECONDS"] == "998920000000" and kv["INSTRUMENT"] == "PAF-BMF"
+    gro = re.search(r"udp_gro (on|off)\s+messages (\d+) \(([0-9.]+) frames per message\)", log)
+    assert gro, log
+    if variant.endswith("plain"):
+        assert gro.group(1) == "off" and float(gro.group(3)) <= 1.0
+    elif gro.group(1) == "on":                          # a kernel without UDP_GRO falls back to "off"
+        assert float(gro.group(3)) > 1.5                # several frames per message did arrive coalesced
 
 
-def test_capture_zero_fills_injected_loss(tmp_path, oracle_mod):
+def test_stock_capture_uses_only_the_calls_the_reference_capture_makes(tmp_path):
+    """-DB2P_STOCK_PSRDADA: the object refers to no ring symbol beyond stock PSRDADA's (the block
+    calls are the reference's two, capture.c:316 and sync.c:101-109) — in particular not to this
+    repo's ipcbuf_get_write_ahead — so it links against -lpsrdada as it stands."""
+    obj = tmp_path / "cap_stock.o"
+    subprocess.run(["gcc", "-O1", "-std=gnu11", "-DB2P_STOCK_PSRDADA", "-DB2P_NO_SHIM_EXTENSIONS", "-c", "-o", str(obj),
+                    os.path.join(PKG, "host", "paf_capture.c")], check=True)
+    und = subprocess.run(["nm", "-u", str(obj)], check=True, capture_output=True, text=True).stdout.split()
+    ring = sorted(x for x in und if x.startswith(("ipcbuf_", "ipcio_", "dada_hdu_", "ascii_header_", "multilog", "fileread")))
+    stock = {"ipcio_open_block_write", "ipcio_close_block_write", "ipcbuf_get_bufsz", "ipcbuf_get_next_write",
+             "ipcbuf_mark_filled", "ipcbuf_enable_sod", "ipcbuf_disable_sod", "dada_hdu_create", "dada_hdu_set_key",
+             "dada_hdu_connect", "dada_hdu_lock_write", "dada_hdu_unlock_write", "dada_hdu_disconnect",
+             "dada_hdu_destroy", "ascii_header_set", "multilog", "multilog_open", "multilog_add", "multilog_close",
+             "fileread"}
+    assert "ipcbuf_get_write_ahead" not in ring
+    assert set(ring) <= stock, sorted(set(ring) - stock)
+    assert {"ipcio_open_block_write", "ipcio_close_block_write"} <= set(ring)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_capture_zero_fills_injected_loss(tmp_path, oracle_mod, variant):
     ndf_block, ncap = 8, 24
-    data, log, rep = _capture_run(tmp_path, ndf_block, ncap, ncap + 2, seed=3, drop_every=7)
+    data, log, rep = _capture_run(tmp_path, ndf_block, ncap, ncap + 2, seed=3, drop_every=7, variant=variant)
     pay = data[4096:]
     want = oracle_mod.synth_fill(ncap, seed=3, mode=1)
     dropped = 0

@@ -32,6 +32,20 @@ def test_header_template_matches_reference_key_for_key():
     assert os.path.getsize(os.path.join(CONF, "header_baseband2power.txt")) < 4096
 
 
+def test_drop_in_artefacts_are_byte_identical_to_the_reference():
+    """header_baseband2power.txt:1-45 and paf-baseband2power.conf:1-26 are shipped verbatim: the
+    sha256 of each shipped file equals the one recorded from /root/reference by
+    tools/make_golden.py — and, where the reference tree is present, the file itself."""
+    ref = _load("reference_artifacts.json")
+    for name in ("header_baseband2power.txt", "paf-baseband2power.conf"):
+        data = open(os.path.join(CONF, name), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == ref["sha256"][name], name
+        assert len(data) == ref["bytes"][name]
+        live = os.path.join("/root/reference", name)
+        if os.path.exists(live):
+            assert data == open(live, "rb").read()
+
+
 def test_conf_matches_reference_key_for_key():
     ref = _load("reference_artifacts.json")["conf"]
     c = configparser.ConfigParser()

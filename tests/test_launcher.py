@@ -80,3 +80,30 @@ def test_two_beam_pipeline_through_the_launcher(tmp_path, oracle_mod, b2p):
         for i in range(nblk):
             want = oracle_mod.finish(oracle_mod.accumulate_omp(payload[i * per:(i + 1) * per]))
             assert np.array_equal(spectra[i].view(np.uint32), want.view(np.uint32)), (b, i)
+
+
+def test_launcher_does_not_hang_when_the_stage_dies(tmp_path):
+    """ADVICE r1: paf_baseband2power exits at once (no usable GPU: CUDA_VISIBLE_DEVICES=-1 via -d);
+    paf_diskdb would then block for ever on a ring nobody reads and paf_dbdisk on a header that
+    never comes.  The launcher must notice, stop the siblings, destroy the rings, return non-zero."""
+    import time
+    ndf_block = 4
+    hdr = os.path.join(PKG, "conf", "header_baseband2power.txt")
+    subprocess.run([os.path.join(BIN, "b2p_gen"), "-o", str(tmp_path / "x.dada"), "-n", str(ndf_block * 12),
+                    "-s", "1", "-H", hdr], check=True, capture_output=True)
+    script = os.path.join(PKG, "scripts", "paf-baseband2power.py")
+    t0 = time.monotonic()
+    r = subprocess.run([sys.executable, script, "-a", CONF, "-b", str(tmp_path), "-c", "0", "-d", "-1", "-e", "0",
+                        "-f", "x.dada", "--ndf", str(ndf_block), "--nblk", "3"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert time.monotonic() - t0 < 60
+    # the rings are gone: connecting to the input key fails
+    chk = subprocess.run([os.path.join(BIN, "paf_diskdb"), "-a", "dada", "-b", str(tmp_path), "-c", "x.dada", "-d", hdr],
+                         capture_output=True, text=True, timeout=30)
+    assert chk.returncode != 0 and "Can not connect to hdu" in chk.stderr
+
+
+def test_spread_plan_places_beams_across_the_box(tmp_path):
+    c = launcher.read_conf(CONF)
+    plans = launcher.plan(c, str(tmp_path), [f"b{i}.dada" for i in range(4)], [], pin=False, ngpus_box=8)
+    assert [p.gpu for p in plans] == [0, 2, 4, 6]

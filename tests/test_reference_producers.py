@@ -173,10 +173,10 @@ def test_paf_capture_agrees_with_the_reference_paf_capture(tmp_path, oracle_mod)
         pytest.skip("needs CAP_NET_ADMIN (loopback alias) and a UTS namespace")
     ndf_block, seed = 16, 77
     (tmp_path / "epoch.txt").write_text("# epoch  days since 1970-01-01\n37 17714.0 2018-07-02\n")
-    results = {}
-    for who in ("ref", "our"):
+    def one_run(who, attempt):
+        """-> capture file as bytes, or None when the capture process hung"""
         key = _key()
-        d = tmp_path / who
+        d = tmp_path / f"{who}{attempt}"
         d.mkdir()
         run(os.path.join(BIN, "paf_dada_db"), "-k", key, "-b", str(ndf_block * FRAME), "-n", "16")   # more blocks than the capture fills: a missed slot stays zero
         sink = cap = None
@@ -188,12 +188,12 @@ def test_paf_capture_agrees_with_the_reference_paf_capture(tmp_path, oracle_mod)
             if who == "ref":
                 cmd = ["unshare", "--uts", "sh", "-c", "hostname pacifix0; exec \"$0\" \"$@\"", os.path.join(REF, "ref_paf_capture")] + common
             else:
-                cmd = [os.path.join(BIN, "paf_capture")] + common + ["-I", "10.17.0.1", "-t", "3"]
+                cmd = [os.path.join(BIN, who_exe[who])] + common + ["-I", "10.17.0.1", "-t", "3"]
             cap = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
             time.sleep(0.7)
             run(os.path.join(BIN, "bmf_replay"), "-D", "10.17.0.1", "-p", "17100", "-n", "2500", "-s", str(seed), "-r", "1500", "-C", "2500")
             try:
-                rc = cap.wait(timeout=40)
+                rc = cap.wait(timeout=25)
             except subprocess.TimeoutExpired:
                 hung = True          # the reference has unsynchronised shared state (sync.c:109 vs capture.c:542)
                 rc = None
@@ -206,10 +206,22 @@ def test_paf_capture_agrees_with_the_reference_paf_capture(tmp_path, oracle_mod)
                     p_.kill()
                     p_.wait()
             run(os.path.join(BIN, "paf_dada_db"), "-d", "-k", key)
-        if hung:
-            assert who == "ref", "this repo's paf_capture must never hang"
-            pytest.skip("the reference paf_capture hung on this run (its own races); nothing to compare against")
-        results[who] = np.fromfile(d / "cap.dada", dtype=np.uint8)
+        return None if hung else np.fromfile(d / "cap.dada", dtype=np.uint8)
+
+    who_exe = {"our": "paf_capture", "our_stock": "paf_capture_stock"}
+    results, attempts = {}, {}
+    for who in ("ref", "our", "our_stock"):
+        # the reference binary hangs now and then (its own races); it gets 5 tries and the
+        # number needed is recorded — this repo's captures get one and must not need another
+        for attempt in range(1, (5 if who == "ref" else 1) + 1):
+            data = one_run(who, attempt)
+            if data is not None:
+                results[who], attempts[who] = data, attempt
+                break
+        assert who in results, (f"{who}: hung in every attempt" if who == "ref"
+                                else "this repo's paf_capture must never hang")
+    print("attempts needed:", attempts)
+    (tmp_path / "attempts.json").write_text(__import__("json").dumps(attempts))
 
     for who, data in results.items():
         kv, idf_start, offsets, matched, zero = _captured_stream(data, seed, oracle_mod)
@@ -220,7 +232,7 @@ def test_paf_capture_agrees_with_the_reference_paf_capture(tmp_path, oracle_mod)
         # every packet that is in the ring sits at (idf*48 + chunk)*7168 (capture.c:540-542):
         # a slot holds the generator's packet for its own (frame, chunk), or nothing
         unexplained = ~(matched | zero)
-        if who == "our":
+        if who.startswith("our"):
             assert not unexplained.any()
             assert offsets == [0] * 6          # one reference frame for all ports
             assert matched.mean() > 0.9

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.json (run in the build container, where /root/reference exists).
 
-  reference_artifacts.json  key/value content of the reference's header template and conf
+  reference_artifacts.json  sha256 + key/value content of the reference's header template and conf
                             (header_baseband2power.txt, paf-baseband2power.conf) — the
-                            drop-in artefacts our copies must match key for key.
+                            drop-in artefacts, which this repo ships byte for byte.
   bmf_hdr_vectors.json      BMF packet-header decode vectors produced by the REFERENCE's own
                             hdr.c (the one source file that compiles standalone), built by
                             oracle/Makefile into oracle/_ref/libpafhdr_ref.so.
@@ -51,10 +51,18 @@ def conf_dict(path):
     return {s: dict(c[s]) for s in c.sections()}
 
 
+def _sha256(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
 def reference_artifacts():
+    hdr, conf = os.path.join(REF, "header_baseband2power.txt"), os.path.join(REF, "paf-baseband2power.conf")
     return {"source": "xinpingdeng/paf-baseband2power: header_baseband2power.txt, paf-baseband2power.conf",
-            "header_kv": header_kv(os.path.join(REF, "header_baseband2power.txt")),
-            "conf": conf_dict(os.path.join(REF, "paf-baseband2power.conf"))}
+            # the two drop-in artefacts are shipped byte for byte
+            "sha256": {"header_baseband2power.txt": _sha256(hdr), "paf-baseband2power.conf": _sha256(conf)},
+            "bytes": {"header_baseband2power.txt": os.path.getsize(hdr), "paf-baseband2power.conf": os.path.getsize(conf)},
+            "header_kv": header_kv(hdr),
+            "conf": conf_dict(conf)}
 
 
 class HdrT(ctypes.Structure):  # hdr.h:6-14

@@ -22,7 +22,8 @@ LINE_FPS = 1.0 / 1.08e-4
 
 
 def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300, keys=None, port=None,
-        nbufs=4, ndf_integration=0, start_barrier=None, settle_s=3.0):
+        nbufs=4, ndf_integration=0, start_barrier=None, settle_s=3.0, gso=8, capture="paf_capture",
+        capture_args=()):
     """One beam: bmf_replay -> UDP loopback -> paf_capture -> ring -> paf_baseband2power -> ring ->
     paf_dbdisk.  `keys`/`port` keep side-by-side beams (one per GPU) apart: own ring pair, own six
     UDP ports (capture.h:22-24 has one port set per NIC; here one per beam on loopback)."""
@@ -46,14 +47,14 @@ def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300, keys=
         if ndf_integration:
             scmd += ["-n", str(ndf_integration)]
         stage = subprocess.Popen(scmd, stderr=subprocess.PIPE)
-        cap = subprocess.Popen([os.path.join(BIN, "paf_capture"), "-a", kin, "-b", "1", "-c", str(ndf), "-d", "0", "-f", HDR, "-g", "none",
+        cap = subprocess.Popen([os.path.join(BIN, capture), *capture_args, "-a", kin, "-b", "1", "-c", str(ndf), "-d", "0", "-f", HDR, "-g", "none",
                                 "-i", "1340.5", "-j", repr(nframes * 1.08e-4), "-k", d, "-I", "127.0.0.1", "-p", str(port), "-t", "5"],
                                stderr=subprocess.PIPE)
         time.sleep(settle_s)   # the stage page-locks the ring (GBs) before it reads
         if start_barrier is not None:
             start_barrier()
         rep = q(os.path.join(BIN, "bmf_replay"), "-D", "127.0.0.1", "-p", str(port), "-n", str(nframes + 64), "-s", "5",
-                "-r", repr(LINE_FPS * rate_frac), "-C", "512", "-T", str(threads))
+                "-r", repr(LINE_FPS * rate_frac), "-C", "512", "-T", str(threads), "-G", str(gso))
         cap.wait(timeout=timeout)
         rc = stage.wait(timeout=timeout)
         sink.wait(timeout=timeout)
@@ -66,9 +67,10 @@ def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300, keys=
     slog = open(os.path.join(d, "paf_baseband2power.log")).read()
     m = re.search(r"blocks (\d+)\s+frames received (\d+)\s+expected (\d+)\s+missing\(zero-filled\) (\d+)\s+late (\d+).*in ([0-9.]+) s", clog)
     s = re.search(r"END: (\d+) blocks in, (\d+) spectra out, ([0-9.]+) s busy", slog)
+    gro = re.search(r"udp_gro (on|off)\s+messages (\d+) \(([0-9.]+) frames per message\)\s+blocked on a full ring ([0-9.]+) s", clog)
     r = re.search(r"(\d+) packets sent.*in ([0-9.]+) s \(([0-9.]+) frames/s, ([0-9.]+) GB/s, ([0-9.]+)x line rate", rep.stdout)
     out = {"path": "bmf_replay -> UDP loopback -> paf_capture -> ring -> paf_baseband2power -> ring -> paf_dbdisk",
-           "gpu": gpu, "udp_port_base": port, "ndf_per_block": ndf, "blocks_requested": nblocks, "rate_frac_requested": rate_frac, "sender_threads": threads}
+           "gpu": gpu, "udp_port_base": port, "capture": capture, "sender_gso_frames": gso, "ndf_per_block": ndf, "blocks_requested": nblocks, "rate_frac_requested": rate_frac, "sender_threads": threads}
     if r:
         out.update({"packets_sent": int(r.group(1)), "replay_s": float(r.group(2)), "replay_GBps": float(r.group(4)),
                     "replay_x_line_rate": float(r.group(5))})
@@ -76,6 +78,9 @@ def run(ndf=8192, nblocks=3, rate_frac=1.0, threads=6, gpu=0, timeout=300, keys=
         out.update({"capture_blocks": int(m.group(1)), "packets_received": int(m.group(2)), "packets_expected": int(m.group(3)),
                     "packets_zero_filled": int(m.group(4)), "packets_late": int(m.group(5)), "capture_s": float(m.group(6)),
                     "received_frac": round(int(m.group(2)) / max(1, int(m.group(3))), 4)})
+    if gro:
+        out.update({"udp_gro": gro.group(1), "frames_per_recv_message": float(gro.group(3)),
+                    "capture_blocked_on_ring_s": float(gro.group(4))})
     if s:
         out.update({"stage_blocks": int(s.group(1)), "spectra": int(s.group(2)), "stage_busy_s": float(s.group(3))})
         t_data = int(s.group(1)) * ndf * 1.08e-4
@@ -90,5 +95,9 @@ if __name__ == "__main__":
     ap.add_argument("--nblocks", type=int, default=3)
     ap.add_argument("--rate", type=float, default=1.0, help="fraction of the BMF line rate (9259 frames/s)")
     ap.add_argument("--threads", type=int, default=6)
+    ap.add_argument("--gso", type=int, default=8, help="frames per send call of the replayer (1 = plain sendmsg)")
+    ap.add_argument("--capture", default="paf_capture", help="paf_capture | paf_capture_stock")
+    ap.add_argument("--no-gro", action="store_true")
     a = ap.parse_args()
-    print(json.dumps(run(a.ndf, a.nblocks, a.rate, a.threads)))
+    print(json.dumps(run(a.ndf, a.nblocks, a.rate, a.threads, gso=a.gso, capture=a.capture,
+                         capture_args=("-G", "0") if a.no_gro else ())))
