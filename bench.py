@@ -661,15 +661,19 @@ def main():
 # --------------------------------------------------------------------------- legs (N-rank aware)
 
 def _channel_group_e2e(R, links, by_beam_spec, src_rot):
-    """Every GPU takes chunks [first_r, first_r + n_r) of EVERY beam, n_r in proportion to its
-    measured host-link rate; the blocks live in SysV shared memory (as ring blocks do) and are
-    page-locked by every rank.  Returns timings for one beam over N GPUs and for N beams."""
+    """Channel-group sharding across the ranks: the (beam, chunk) units of a step — laid out
+    beam-major — are cut into one run per GPU in proportion to what its host link delivers, so
+    unequal links finish together; a GPU reads its chunk columns straight out of the full-frame
+    blocks (strided H2D).  The blocks live in SysV shared memory (as ring blocks do) and are
+    page-locked by every rank that reads them.  The shares start from the link probe and are
+    refined from the measured per-GPU completion times of a few untimed steps (links that share
+    a host bridge slow each other down, which no solo probe sees).  Returns timings for one
+    beam over N GPUs and for N beams over N GPUs."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from paf_baseband2power_b200 import Baseband2Power
-    from paf_baseband2power_b200 import api as b2p_api
-    from paf_baseband2power_b200.sharding import gather_channel_groups
+    from paf_baseband2power_b200.sharding import gather_unit_ranges, plan_units
     rank, world, gpu, lib, blk, ndf, g, args = R.rank, R.world, R.gpu, R.lib, R.blk, R.ndf, R.g, R.args
 
     base = [0]
@@ -682,37 +686,76 @@ def _channel_group_e2e(R, links, by_beam_spec, src_rot):
     assert rc == 0
     R.host_barrier()
     blocks = [mine if r == rank else SysVBlock(base[0] + r, blk, create=False) for r in range(world)]
-    t_reg = time.perf_counter()
-    for b in blocks:
-        rc = lib.b2p_host_register(b.ptr, blk)
-        assert rc == 0, "cudaHostRegister of a shared beam block failed"
-    t_reg = time.perf_counter() - t_reg
-    counts = b2p_api.split_chunks(links, world, 48)
-    first = sum(counts[:rank])
-    out = {"link_GBps": [round(x, 2) for x in links], "chunks_per_gpu": counts,
-           "register_s_per_rank": round(t_reg, 2),
-           "host_blocks": "SysV shared memory, one 2.8 GB block per beam, page-locked by every rank"}
+    registered = set()
+    t_reg = [0.0]
 
-    def run_mode(nb, steps):
-        ctx = None
-        if counts[rank] > 0:
-            ctx = Baseband2Power(device_id=gpu, nbeam=nb, kernel=args.kernel, nchunk=counts[rank],
-                                 first_chunk=first, nchunk_total=48)
-        ptrs = [blocks[b].ptr for b in range(nb)]
+    def need(beam):
+        if beam not in registered:
+            t0 = time.perf_counter()
+            rc = lib.b2p_host_register(blocks[beam].ptr, blk)
+            assert rc == 0, "cudaHostRegister of a shared beam block failed"
+            t_reg[0] += time.perf_counter() - t0
+            registered.add(beam)
+
+    def all_gather(x: float) -> list:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        outl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outl, t)
+        return [float(o.item()) for o in outl]
+
+    out = {"link_GBps_probe": [round(x, 2) for x in links],
+           "host_blocks": "SysV shared memory, one 2.8 GB block per beam, page-locked by the ranks that read it"}
+
+    def run_mode(nb, steps, refine):
+        shares = list(links)
+        history = []
+        ctxs, plan = [], None
+
+        def build(shares):
+            nonlocal ctxs, plan
+            for *_, c in ctxs:
+                c.close()
+            plan = plan_units(shares, nb, 48)
+            ctxs = []
+            for beam, first, n in plan[rank]:
+                need(beam)
+                ctxs.append((beam, first, n, Baseband2Power(device_id=gpu, nbeam=1, kernel=args.kernel, nchunk=n,
+                                                            first_chunk=first, nchunk_total=48)))
 
         def one():
-            sp = np.zeros((nb, 0), dtype=np.float32)
-            if ctx is not None:
-                ctx.accumulate_host_async(ptrs, ndf, finish=True)
-                sp = ctx.wait_output()                          # [nb][counts[rank]*7]
-            return gather_channel_groups(sp, counts, 7, group=R.host_pg)   # 1344 B per beam per rank
+            """-> (spectra on rank 0, this rank's seconds from first issue to last spectrum)"""
+            t0 = time.perf_counter()
+            for beam, first, n, c in ctxs:                 # queue everything, then wait
+                c.accumulate_host_async([blocks[beam].ptr], ndf, finish=True)
+            part = np.zeros((nb, g.nchan), dtype=np.float32)
+            for beam, first, n, c in ctxs:
+                part[beam, 7 * first:7 * (first + n)] = c.wait_output()[0]
+            busy = time.perf_counter() - t0
+            return gather_unit_ranges(part, plan, 7, group=R.host_pg), busy   # 1344 B per beam per rank
 
-        for _ in range(2):
-            full = one()
+        build(shares)
+        for it in range(refine + 1):
+            R.barrier()
+            one()                                           # warm (staging buffers, first touch)
+            R.barrier()
+            _, busy = one()
+            times = all_gather(busy)
+            units = [sum(n for _, _, n in plan[r]) for r in range(world)]
+            history.append({"units_per_gpu": units, "busy_ms_per_gpu": [round(t * 1e3, 2) for t in times]})
+            live = [t for t, u in zip(times, units) if u > 0]
+            if it == refine or max(live) / min(live) < 1.04:
+                break
+            # what each link delivered under the real contention of this step
+            rate = [u / t if u > 0 else 0.0 for u, t in zip(units, times)]
+            # a GPU that got no unit keeps its probe rate scaled like the others
+            scale = sum(r_ for r_ in rate if r_ > 0) / max(1e-9, sum(l for l, r_ in zip(links, rate) if r_ > 0))
+            new = [r_ if r_ > 0 else l * scale for r_, l in zip(rate, links)]
+            shares = [0.5 * (a / sum(shares)) + 0.5 * (b_ / sum(new)) for a, b_ in zip(shares, new)]   # damped
+            build(shares)
         R.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            full = one()
+            full, _ = one()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         R.barrier()
@@ -720,25 +763,31 @@ def _channel_group_e2e(R, links, by_beam_spec, src_rot):
         ok = None
         if rank == 0 and by_beam_spec is not None:
             ok = bool(np.array_equal(full.view(np.uint32), np.asarray(by_beam_spec)[:nb].view(np.uint32)))
-        if ctx is not None:
-            ctx.close()
+        units = [sum(n for _, _, n in plan[r]) for r in range(world)]
+        for *_, c in ctxs:
+            c.close()
+        ctxs = []
         return {"beams_per_step": nb, "value": round(nb * blk / (ms * 1e-3) / 1e9, 3), "unit": UNIT,
                 "ms_per_step": round(ms, 3), "steps": steps,
                 "realtime_factor": round(nb * g.t_integration_s * ndf / BLOCK_NDF / (ms * 1e-3), 2),
+                "units_per_gpu": units, "units_total": nb * 48, "unit_is": "one chunk column of one beam (58.7 MB)",
+                "plan": [[list(x) for x in plan[r]] for r in range(world)],
+                "refinement": history,
                 "bit_identical_to_by_beam_spectra": ok,
-                "path": f"b2p_accumulate_host_async + b2p_wait_output on one chunk-group shard per GPU (strided H2D, "
-                        f"pitch 344064 B; chunks per GPU {counts} from the measured link rates) + gloo gather of the channel ranges"}
+                "path": "b2p_accumulate_host_async + b2p_wait_output on chunk-group shard contexts (strided H2D, pitch 344064 B); "
+                        "(beam, chunk) units per GPU from the link probe, refined from measured completion times; "
+                        "gloo gather of the channel ranges"}
 
     try:
-        out["single_beam"] = run_mode(1, max(4, R.ke))      # one beam's block over N host links
-        out["all_beams"] = run_mode(world, max(4, R.ke // 2))
-        if rank == 0:
-            for k in ("single_beam", "all_beams"):
-                if out[k]["bit_identical_to_by_beam_spectra"] is False:
-                    raise SystemExit("bench.py: channel-group spectra differ from the by-beam spectra — number withheld")
+        out["single_beam"] = run_mode(1, max(4, R.ke), 3)       # one beam's block over N host links
+        out["all_beams"] = run_mode(world, max(4, R.ke // 2), 4)
+        out["register_s_per_rank"] = round(t_reg[0], 2)
+        for k in ("single_beam", "all_beams"):
+            if rank == 0 and out[k]["bit_identical_to_by_beam_spectra"] is False:
+                raise SystemExit("bench.py: channel-group spectra differ from the by-beam spectra — number withheld")
     finally:
-        for b in blocks:
-            lib.b2p_host_unregister(b.ptr)
+        for beam in registered:
+            lib.b2p_host_unregister(blocks[beam].ptr)
         R.host_barrier()
         for b in blocks:
             b.close()
@@ -797,7 +846,10 @@ def _ring_leg(R):
         out.update({"aggregate_GBps": round(total / busy / 1e9, 3),
                     "aggregate_realtime_factor": round(t_data / busy, 2),
                     "slowest_stage_busy_s": busy,
-                    "per_rank_GBps": [r.get("stage_GBps") for r in allres]})
+                    "sum_of_per_rank_GBps": round(sum(r["stage_GBps"] for r in good), 3),
+                    "per_rank_GBps": [r.get("stage_GBps") for r in allres],
+                    "note": "aggregate = all bytes / the slowest pipeline's busy time; the pipelines are independent, "
+                            "so while all run the box ingests the sum of the per-rank rates"})
         if world == 1:                              # same keys as in round 1's line
             out.update({k: v for k, v in good[0].items() if k not in ("rank",)})
     out["per_rank"] = allres

@@ -135,3 +135,59 @@ def gather_channel_groups(local: np.ndarray, counts: Sequence[int], nch_per_chun
         sl = slice(f * nch_per_chunk, (f + m) * nch_per_chunk)
         out[:, sl] = bufs[r].numpy()[:, sl]
     return out
+
+
+def plan_units(shares: Sequence[float], nbeams: int, nchunk: int = 48) -> List[List[tuple]]:
+    """Finer than whole chunk columns: the nbeams*nchunk (beam, chunk) units, laid out
+    beam-major, are cut into len(shares) consecutive runs in proportion to `shares`; shard r
+    gets, per beam it touches, one interval (beam, first_chunk, nchunk).  With 8 beams a unit
+    is 1/384 of the step instead of the 1/48 of a chunk column, so unequal host links can be
+    matched to ~1 %.  Returns one interval list per shard (possibly empty)."""
+    w = [float(x) for x in shares]
+    if not w or any(x < 0 for x in w) or sum(w) <= 0:
+        raise ValueError("shares must be non-negative and not all zero")
+    total = nbeams * nchunk
+    bounds, acc = [0], 0.0
+    for x in w[:-1]:
+        acc += x / sum(w)
+        bounds.append(min(total, max(bounds[-1], int(round(acc * total)))))
+    bounds.append(total)
+    plan = []
+    for r in range(len(w)):
+        lo, hi = bounds[r], bounds[r + 1]
+        items = []
+        while lo < hi:
+            beam, first = divmod(lo, nchunk)
+            n = min(hi - lo, nchunk - first)
+            items.append((beam, first, n))
+            lo += n
+        plan.append(items)
+    return plan
+
+
+def gather_unit_ranges(local: np.ndarray, plan: Sequence[Sequence[tuple]], nch_per_chunk: int = 7, group=None,
+                       dst: int = 0):
+    """`local` is this rank's [nbeams, nchan] array with its own (beam, chunk-range) intervals of
+    `plan` filled in; returns the complete [nbeams, nchan] on `dst` (None elsewhere).  Intervals
+    are disjoint, so this is a placement of 1344-byte rows, not a reduction."""
+    import torch
+    import torch.distributed as dist
+
+    local = np.ascontiguousarray(local, dtype=np.float32)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local.copy()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if len(plan) != world:
+        raise ValueError("one interval list per rank")
+    t = torch.from_numpy(local)
+    bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = np.zeros_like(local)
+    for r, items in enumerate(plan):
+        src = bufs[r].numpy()
+        for beam, first, n in items:
+            sl = slice(first * nch_per_chunk, (first + n) * nch_per_chunk)
+            out[beam, sl] = src[beam, sl]
+    return out

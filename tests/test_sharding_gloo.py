@@ -162,3 +162,46 @@ def test_gpu_placement_spreads_ranks():
         for ngpu in range(world, 17):
             gpus = [gpu_for_rank(r, world, ngpu) for r in range(world)]
             assert len(set(gpus)) == world and max(gpus) < ngpu
+
+
+def _unit_worker(rank, world, port, shares, nbeams, q):
+    import oracle
+    from paf_baseband2power_b200.sharding import gather_unit_ranges, plan_units
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = plan_units(shares, nbeams)
+    part = np.zeros((nbeams, 336), np.float32)
+    for beam, first, n in plan[rank]:
+        blk = oracle.synth_fill(NDF, seed=800 + beam, mode=1).reshape(NDF, 48, 7168)
+        sub = np.ascontiguousarray(blk[:, first:first + n]).reshape(-1)
+        part[beam, 7 * first:7 * (first + n)] = oracle.finish(oracle.accumulate(sub, NDF, oracle.Geometry(nchunk=n)), 1.0)
+    out = gather_unit_ranges(part, plan)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shares,nbeams", [([1, 1], 2), ([26, 43, 35], 3), ([1, 0, 2], 2), ([5, 1], 1)])
+def test_unit_plan_gather_over_gloo(shares, nbeams):
+    """(beam, chunk) units cut into one run per rank: every rank integrates its intervals, rank 0
+    places them; equal to the oracle's spectra of the whole blocks."""
+    import oracle
+    from paf_baseband2power_b200.sharding import plan_units
+    world = len(shares)
+    plan = plan_units(shares, nbeams)
+    covered = sorted((b, c) for items in plan for b, f, n in items for c in range(f, f + n))
+    assert covered == [(b, c) for b in range(nbeams) for c in range(48)]      # a partition, nothing twice
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_unit_worker, args=(r, world, port, shares, nbeams, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([oracle.finish(oracle.accumulate(oracle.synth_fill(NDF, seed=800 + b, mode=1)), 1.0) for b in range(nbeams)])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
