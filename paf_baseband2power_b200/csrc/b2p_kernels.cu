@@ -228,20 +228,26 @@ template <int ID, int COUNT> __device__ __forceinline__ void epi_bar()
 
 /*
  * Arrival: every CTA that has stored the partial sums of one (beam, column) item calls
- * this with all `nt` participating threads; the partial stores must precede it in program
+ * this with all participating threads; the partial stores must precede it in program
  * order in the threads that made them.  Returns true (to all threads) in the one CTA that
  * arrived last — the partial sums of all nsplit splits of the column are then visible.
+ * One acq_rel atomic by one thread after a CTA barrier: the barrier puts the CTA's stores
+ * before the atomic (release, cumulative), the atomic's acquire side and the second barrier
+ * put the other CTAs' stores before the reads of the last CTA — no per-thread fences.
  */
 template <int ID, int COUNT>
 __device__ __forceinline__ bool column_arrive(unsigned int *cnt, uint32_t nsplit, uint32_t *flag,
                                               int tid)
 {
-  __threadfence(); /* release: this thread's partial sums before the arrival */
   epi_bar<ID, COUNT>();
-  if (tid == 0) *flag = (atomicAdd(cnt, 1u) == nsplit - 1u) ? 1u : 0u;
+  if (tid == 0) {
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
+    *flag = (old == nsplit - 1u) ? 1u : 0u;
+  }
   epi_bar<ID, COUNT>();
   const bool last = *flag != 0u;
-  if (last) __threadfence(); /* acquire side */
+  if (last) __threadfence(); /* once per column: belt and braces on the acquire side */
   return last;
 }
 
@@ -251,7 +257,8 @@ __device__ __forceinline__ bool column_arrive(unsigned int *cnt, uint32_t nsplit
  * order; ncol threads then add the LP lane sums in ascending order and the running
  * accumulator — a fixed order whoever arrives last.  finish: emit (float)total*scale (one RN
  * conversion, one fp32 multiply) and clear the accumulator; otherwise store the total back.
- * Partial sums were written by other SMs: read them at L2 (ld.global.cg).
+ * Partial sums were written by other SMs: read them at L2 (ld.global.cg), eight loads in
+ * flight per thread so the fold costs about one L2 round trip, not one per split.
  */
 template <typename T, int ID, int COUNT>
 __device__ __forceinline__ void column_fold(const T *__restrict__ partials, T *fold, const B2pFold &F,
@@ -261,11 +268,23 @@ __device__ __forceinline__ void column_fold(const T *__restrict__ partials, T *f
 {
   int LP = nt / ncol;
   if (LP > 32) LP = 32;
+  T *acc = (T *)F.acc;
+  T prev = 0;
+  if (tid < ncol) prev = acc[(size_t)row * nchan + col0 + tid]; /* in flight under the fold */
   if (tid < LP * ncol) {
     const int ch = tid % ncol, l = tid / ncol;
     const T *p = partials + (size_t)lbeam * nsplit * nchan + col0 + ch;
     T v = 0;
-    for (uint32_t sp = l; sp < nsplit; sp += LP) v += __ldcg(p + (size_t)sp * nchan);
+    for (uint32_t sp = l; sp < nsplit; sp += 8u * LP) {
+      T x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t q = sp + (uint32_t)u * LP;
+        x[u] = q < nsplit ? __ldcg(p + (size_t)q * nchan) : (T)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += x[u]; /* ascending split order */
+    }
     fold[tid] = v;
   }
   epi_bar<ID, COUNT>();
@@ -273,8 +292,7 @@ __device__ __forceinline__ void column_fold(const T *__restrict__ partials, T *f
     T tot = 0;
     for (int l = 0; l < LP; ++l) tot += fold[l * ncol + tid];
     const size_t idx = (size_t)row * nchan + col0 + tid;
-    T *acc = (T *)F.acc;
-    tot += acc[idx];
+    tot += prev;
     if (F.finish) {
       F.out[idx] = __fmul_rn(to_f32_rn(tot), F.scale);
       acc[idx] = 0;
@@ -284,6 +302,17 @@ __device__ __forceinline__ void column_fold(const T *__restrict__ partials, T *f
   }
   if (tid == 0) *cnt = 0u; /* clean for the next launch (and for a CUDA-graph replay) */
   epi_bar<ID, COUNT>();    /* `fold` may be reused by the caller */
+}
+
+/* Out of line for the persistent TMA kernel: the fold runs a handful of times per CTA and must
+   not cost the streaming loop registers (480 threads leave 128 per thread). */
+template <typename T, int ID, int COUNT>
+__device__ __noinline__ void column_fold_call(const T *partials, T *fold, const B2pFold *F,
+                                              uint32_t lbeam, int row, uint32_t nsplit, uint32_t nchan,
+                                              uint32_t col0, int ncol, int tid, unsigned int *cnt)
+{
+  __threadfence();
+  column_fold<T, ID, COUNT>(partials, fold, *F, lbeam, row, nsplit, (size_t)nchan, col0, ncol, tid, COUNT, cnt);
 }
 
 /* ------------------------------------- LDG.256 kernel, BMF geometry (default) */
@@ -514,7 +543,8 @@ template <int G, int NSTAGE> struct TmaSmem {
   static constexpr int kRedElems = kTmaConsumerWarps * G * kNchBmf > kTmaConsumers
                                        ? kTmaConsumerWarps * G * kNchBmf
                                        : kTmaConsumers;
-  static constexpr int kFlagOff = kRedOff + kRedElems * 8;
+  static constexpr int kFoldOff = kRedOff + kRedElems * 8; /* scratch of the column fold */
+  static constexpr int kFlagOff = kFoldOff + kTmaConsumers * 8;
   static constexpr int kBytes = kFlagOff + 16;
 };
 
@@ -535,7 +565,9 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t fp
   uint64_t *empty = full + NSTAGE;
   volatile uint32_t *tag = (volatile uint32_t *)(smem + S::kTagOff);
   T *red = (T *)(smem + S::kRedOff);
-  uint32_t *last_flag = (uint32_t *)(smem + S::kFlagOff);
+  T *foldbuf = (T *)(smem + S::kFoldOff);
+  /* [0] != 0: the column of item [1] is complete, fold it at the next item boundary */
+  volatile uint32_t *fold_due = (volatile uint32_t *)(smem + S::kFlagOff);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ngroups = nchunk / G;
@@ -546,6 +578,7 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t fp
       mbar_init(&empty[s], kTmaConsumerWarps);
     }
     mbar_fence_init();
+    fold_due[0] = 0u;
   }
   if (!early) pdl_wait_predecessor();
   __syncthreads();
@@ -637,7 +670,21 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t fp
         v = warp_sum(v);
         if (lane == 0) red[warp * (G * kNchBmf) + g * kNchBmf + ch] = v;
       }
-    consumer_bar();
+    consumer_bar(); /* A: the warp sums of this item are in `red` */
+    /*
+     * Column bookkeeping without stalling the consumers: thread 0 alone does the arrival
+     * atomic of an item (after barrier B below) while the others go on streaming; if that
+     * made a column complete it leaves a note, and everybody folds that column here, at the
+     * next item boundary (or after the last stage).
+     */
+    if (fold_due[0]) {
+      const uint32_t it2 = fold_due[1];
+      const uint32_t g2 = it2 % ngroups, b2 = (it2 / ngroups) / nsplit;
+      column_fold_call<T, 1, kTmaConsumers>(partials, foldbuf, &fold, b2, beams.slot[b2], nsplit,
+                                            (uint32_t)nchan, g2 * G * kNchBmf, G * kNchBmf, tid,
+                                            fold.colcnt + b2 * ngroups + g2);
+      if (tid == 0) fold_due[0] = 0u;
+    }
     /* the previous kernel of the stream has finished with `partials`, the counters and acc */
     if (!waited) pdl_wait_predecessor();
     waited = true;
@@ -646,13 +693,30 @@ b2p_fused_tma_bmf(const B2pBeams beams, const uint32_t nchunk, const uint64_t fp
       for (int w = 0; w < kTmaConsumerWarps; ++w) sum += red[w * (G * kNchBmf) + tid];
       dst[tid] = sum;
     }
-    /* column (beam, chunk group) complete?  its last item folds all nsplit partial sums */
-    unsigned int *cnt = fold.colcnt + beam * ngroups + group;
-    if (column_arrive<1, kTmaConsumers>(cnt, nsplit, last_flag, tid))
-      column_fold<T, 1, kTmaConsumers>(partials, red, fold, beam, beams.slot[beam], nsplit, nchan,
-                                       group * G * kNchBmf, G * kNchBmf, tid, kTmaConsumers, cnt);
+    consumer_bar(); /* B: `red` is free again; the partial sums precede thread 0's arrival */
+    if (tid == 0) {
+      unsigned int old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
+                   : "=r"(old)
+                   : "l"(fold.colcnt + beam * ngroups + group)
+                   : "memory");
+      if (old == nsplit - 1u) { /* last item of its column: all nsplit partial sums are there */
+        fold_due[1] = item;
+        __threadfence_block();
+        fold_due[0] = 1u;
+      }
+    }
 #pragma unroll
     for (int g = 0; g < G; ++g) a[g][0] = a[g][1] = 0;
+  }
+  /* every consumer has seen the end tag; a column completed by this CTA's last item is still due */
+  consumer_bar();
+  if (fold_due[0]) {
+    const uint32_t it2 = fold_due[1];
+    const uint32_t g2 = it2 % ngroups, b2 = (it2 / ngroups) / nsplit;
+    column_fold_call<T, 1, kTmaConsumers>(partials, foldbuf, &fold, b2, beams.slot[b2], nsplit,
+                                          (uint32_t)nchan, g2 * G * kNchBmf, G * kNchBmf, tid,
+                                          fold.colcnt + b2 * ngroups + g2);
   }
 }
 
