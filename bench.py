@@ -380,6 +380,7 @@ def main():
 
     R = Run()
     R.args, R.rank, R.world, R.gpu, R.host_pg = args, rank, world, gpu, host_pg
+    R.gpu_map = gpu_map
     R.vcpus = _host_threads()
 
     def barrier():
@@ -816,6 +817,13 @@ def _ring_plan(world, want_bufs, blk_ndf):
 def _ring_leg(R):
     from paf_baseband2power_b200.sharding import ring_keys_for_beam
     rank, world, gpu, args, ndf = R.rank, R.world, R.gpu, R.args, R.ndf
+    synced = [False]
+
+    def start_together():       # every rank passes this exactly once, also when its pipeline fails
+        if not synced[0]:
+            synced[0] = True
+            R.host_barrier()
+
     try:
         mod = _load_tool("run_ring_e2e")
         ndf_blk, nbufs, _ = _ring_plan(world, 3, ndf)
@@ -824,17 +832,15 @@ def _ring_leg(R):
         keys = ring_keys_for_beam(rank, 0x1B200 + salt, 0x1B2A0 + salt, 0x100)
         res = mod.run(ndf=ndf_blk, nbufs=nbufs, nblocks=args.ring_blocks * per_int, gpu=gpu, kernel=args.kernel,
                       keys=keys, ndf_integration=ndf if per_int > 1 else 0,
-                      producer_threads=max(1, R.vcpus // world), seed=1 + rank, start_barrier=R.host_barrier)
+                      producer_threads=max(1, R.vcpus // world), seed=1 + rank, start_barrier=start_together)
         res.pop("_spectra", None)
         res["rank"] = rank
     except Exception as e:
         res = {"rank": rank, "error": repr(e)[:300]}
-        try:
-            R.host_barrier()
-        except Exception:
-            pass
+    start_together()
     allres = R.gather_objects(res)
     if rank != 0:
+        R.host_barrier()        # rank 0 alone runs the one-stage-all-GPUs pipeline below
         return None
     good = [r for r in allres if "error" not in r]
     out = {"path": "paf_memdb -> ring -> paf_baseband2power -> ring -> paf_dbdisk: one pipeline and one ring pair per GPU, all running at once",
@@ -853,6 +859,19 @@ def _ring_leg(R):
         if world == 1:                              # same keys as in round 1's line
             out.update({k: v for k, v in good[0].items() if k not in ("rank",)})
     out["per_rank"] = allres
+    if world > 1:
+        # one beam, ONE stage process, its channel groups over all GPUs of this run (-d list):
+        # the single-process form of channel-group sharding, through the same rings
+        try:
+            keys = ring_keys_for_beam(world, 0x1B200 + salt, 0x1B2A0 + salt, 0x100)
+            res = mod.run(ndf=ndf_blk, nbufs=nbufs, nblocks=max(8, args.ring_blocks // 2) * per_int,
+                          gpu=",".join(str(x) for x in R.gpu_map), kernel=args.kernel, keys=keys,
+                          ndf_integration=ndf if per_int > 1 else 0, producer_threads=R.vcpus, seed=99)
+            res.pop("_spectra", None)
+            out["single_beam_one_stage_all_gpus"] = res
+        except Exception as e:
+            out["single_beam_one_stage_all_gpus"] = {"error": repr(e)[:300]}
+    R.host_barrier()
     return out
 
 
@@ -870,13 +889,21 @@ def _live_leg(R):
     for ti, rate in enumerate((1.0, 0.5, 0.25)):
         salt = (os.getppid() & 0x3F) * 0x10000 + ti * 0x1000
         keys = ring_keys_for_beam(rank, 0x2C200 + salt, 0x2C2A0 + salt, 0x100)
+        synced = [False]
+
+        def start_together(synced=synced):
+            if not synced[0]:
+                synced[0] = True
+                R.host_barrier()
+
         try:
             res = mod.run(ndf=ndf_blk, nblocks=args.live_blocks * per_int, rate_frac=rate, threads=threads, gpu=gpu,
                           keys=keys, port=21000 + 64 * rank + 8 * ti, nbufs=nbufs,
-                          ndf_integration=ndf if per_int > 1 else 0, start_barrier=R.host_barrier)
+                          ndf_integration=ndf if per_int > 1 else 0, start_barrier=start_together)
             res["rank"] = rank
         except Exception as e:
             res = {"rank": rank, "error": repr(e)[:300]}
+        start_together()
         allres = R.gather_objects(res)
         done = [True]
         if rank == 0:

@@ -154,6 +154,9 @@ int b2p_integrate_host(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf, flo
 int b2p_accumulate_host_async(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf, int finish);
 int b2p_wait_input(b2p_ctx *ctx);
 int b2p_wait_output(b2p_ctx *ctx, float *out_host);
+/* Duration of the H2D copies of the last host call (first copy issued -> last copy done),
+   from CUDA events on the copy stream; synchronises with the last copy. */
+int b2p_last_h2d_ms(b2p_ctx *ctx, double *ms);
 
 /*
  * Zero-copy variant: the fused kernel reads the pinned, device-mapped host
@@ -219,6 +222,10 @@ int  b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t 
 int  b2p_group_integrate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, float *out_host);
 int  b2p_group_finish(b2p_group *g, float *out_host);
 int  b2p_group_reset(b2p_group *g);
+/* Between integrations: move chunks towards the GPUs whose links delivered more during the
+   last host call (H2D time per shard, CUDA events), half way per call.  *changed = 1 when the
+   split moved (the shard contexts are then rebuilt). */
+int  b2p_group_rebalance(b2p_group *g, int *changed);
 int  b2p_group_size(const b2p_group *g);                  /* shards with >= 1 chunk */
 b2p_ctx *b2p_group_ctx(const b2p_group *g, int i);
 int  b2p_group_shard(const b2p_group *g, int i, int *device, int *first_chunk, int *nchunk);

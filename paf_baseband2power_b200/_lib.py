@@ -45,6 +45,7 @@ SYMBOLS = {
     "b2p_accumulate_host_async": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_int]),
     "b2p_wait_input": (c_int, [c_void_p]),
     "b2p_wait_output": (c_int, [c_void_p, c_void_p]),
+    "b2p_last_h2d_ms": (c_int, [c_void_p, POINTER(c_double)]),
     "b2p_accumulate_host_mapped": (c_int, [c_void_p, POINTER(c_void_p), c_uint64]),
     "b2p_finish": (c_int, [c_void_p, c_void_p]),
     "b2p_finish_device": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -70,6 +71,7 @@ SYMBOLS = {
     "b2p_group_integrate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p]),
     "b2p_group_finish": (c_int, [c_void_p, c_void_p]),
     "b2p_group_reset": (c_int, [c_void_p]),
+    "b2p_group_rebalance": (c_int, [c_void_p, POINTER(c_int)]),
     "b2p_group_size": (c_int, [c_void_p]),
     "b2p_group_ctx": (c_void_p, [c_void_p, c_int]),
     "b2p_group_shard": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

@@ -242,6 +242,11 @@ class Baseband2Power:
         _check(self._lib.b2p_wait_output(self._ctx, out.ctypes.data), self._ctx)
         return out
 
+    def last_h2d_ms(self) -> float:
+        ms = c_double()
+        _check(self._lib.b2p_last_h2d_ms(self._ctx, byref(ms)), self._ctx)
+        return ms.value
+
     def accumulate_host_mapped(self, blocks: Sequence, ndf: int | None = None):
         ndf = self._host_ndf(blocks, ndf)
         arr = self._ptr_array(blocks, _host_ptr)
@@ -371,6 +376,12 @@ class ShardGroup:
 
     def reset(self):
         self._check(self._lib.b2p_group_reset(self._g))
+
+    def rebalance(self) -> bool:
+        """Between integrations: shift chunks towards the faster links (measured); True if moved."""
+        ch = c_int()
+        self._check(self._lib.b2p_group_rebalance(self._g, byref(ch)))
+        return bool(ch.value)
 
     def close(self):
         if getattr(self, "_g", None):

@@ -53,6 +53,8 @@ struct b2p_ctx {
   cudaEvent_t copied[B2P_MAX_STAGE_BUFS], consumed[B2P_MAX_STAGE_BUFS];
   uint64_t pieces; /* pieces issued so far over the context's life */
   int out_queued;  /* a D2H of the spectrum is queued on the compute stream */
+  cudaEvent_t h2d_begin, h2d_end; /* around the H2D copies of the last host call (copy stream) */
+  int h2d_timed;
   /* per-launch timing */
   int timing;
   std::vector<cudaEvent_t> ev_pool;
@@ -236,6 +238,8 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   c->compute = c->copy = NULL;
   c->last_stream = NULL;
   c->xev = NULL;
+  c->h2d_begin = c->h2d_end = NULL;
+  c->h2d_timed = 0;
   for (int i = 0; i < B2P_MAX_STAGE_BUFS; ++i) {
     c->stage[i] = NULL;
     c->copied[i] = c->consumed[i] = NULL;
@@ -262,6 +266,8 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
   CKC(cudaEventCreateWithFlags(&c->xev, cudaEventDisableTiming));
+  CKC(cudaEventCreate(&c->h2d_begin));
+  CKC(cudaEventCreate(&c->h2d_end));
   const size_t nacc = (size_t)p->nbeam * c->nchan;
   const size_t ncnt = (size_t)p->nbeam * p->nchunk;
   CKC(cudaMalloc(&c->acc, nacc * c->acc_elem));
@@ -293,6 +299,8 @@ void b2p_destroy(b2p_ctx *c)
   }
   for (size_t i = 0; i < c->ev_pool.size(); ++i) cudaEventDestroy(c->ev_pool[i]);
   if (c->xev) cudaEventDestroy(c->xev);
+  if (c->h2d_begin) cudaEventDestroy(c->h2d_begin);
+  if (c->h2d_end) cudaEventDestroy(c->h2d_end);
   if (c->acc) cudaFree(c->acc);
   if (c->partials) cudaFree(c->partials);
   if (c->out_dev) cudaFree(c->out_dev);
@@ -489,6 +497,7 @@ static int host_issue(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int fi
   if (rc) return rc;
   const uint64_t piece = c->p.stage_ndf;
   const bool compact = c->src_pitch == c->frame_bytes;
+  if (ndf) CK(c, cudaEventRecord(c->h2d_begin, c->copy));
   for (int b = 0; b < c->p.nbeam && ndf; ++b) {
     const unsigned char *src = (const unsigned char *)hptrs[b] + c->src_offset;
     for (uint64_t f0 = 0; f0 < ndf; f0 += piece) {
@@ -511,11 +520,27 @@ static int host_issue(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int fi
       c->pieces++;
     }
   }
+  if (ndf) {
+    CK(c, cudaEventRecord(c->h2d_end, c->copy));
+    c->h2d_timed = 1;
+  }
   if (finish) {
     const size_t bytes = (size_t)c->p.nbeam * c->nchan * sizeof(float);
     CK(c, cudaMemcpyAsync(c->out_pinned, c->out_dev, bytes, cudaMemcpyDeviceToHost, c->compute));
     c->out_queued = 1;
   }
+  return B2P_OK;
+}
+
+int b2p_last_h2d_ms(b2p_ctx *c, double *ms)
+{
+  if (!c || !ms) return B2P_EINVAL;
+  if (!c->h2d_timed) FAIL(c, B2P_ESTATE, "b2p_last_h2d_ms: no host call has been made yet");
+  CK(c, cudaSetDevice(c->p.device_id));
+  float f = 0.f;
+  CK(c, cudaEventSynchronize(c->h2d_end));
+  CK(c, cudaEventElapsedTime(&f, c->h2d_begin, c->h2d_end));
+  *ms = (double)f;
   return B2P_OK;
 }
 
@@ -829,6 +854,11 @@ struct b2p_group {
   b2p_ctx *ctx[B2P_MAX_GROUP];
   int device[B2P_MAX_GROUP], first[B2P_MAX_GROUP], count[B2P_MAX_GROUP];
   int nbeam, nch, nchan_total;
+  /* as given to b2p_group_create, for b2p_group_rebalance */
+  b2p_params base;
+  int ndev, all_devices[B2P_MAX_GROUP], all_counts[B2P_MAX_GROUP];
+  double share[B2P_MAX_GROUP];
+  int open_integration; /* frames accumulated and not yet finished */
   std::vector<float> tmp;
   char err[512];
 };
@@ -838,6 +868,33 @@ static int group_fail(b2p_group *g, int i, int rc)
   snprintf(g->err, sizeof(g->err), "shard %d (gpu %d, chunks %d..%d): %s", i, g->device[i], g->first[i],
            g->first[i] + g->count[i] - 1, b2p_last_error(g->ctx[i]));
   return rc;
+}
+
+/* (re)build the shard contexts of g from g->all_counts */
+static int group_build(b2p_group *g)
+{
+  for (int i = 0; i < g->n; ++i) b2p_destroy(g->ctx[i]);
+  g->n = 0;
+  int first = 0;
+  for (int i = 0; i < g->ndev; ++i) {
+    if (g->all_counts[i] == 0) continue;
+    b2p_params p = g->base;
+    p.device_id = g->all_devices[i];
+    p.nchunk = g->all_counts[i];
+    p.first_chunk = first;
+    p.nchunk_total = g->base.nchunk;
+    p.nsplit = 0;
+    p.stage_ndf = 0;
+    const int k = g->n;
+    g->device[k] = g->all_devices[i];
+    g->first[k] = first;
+    g->count[k] = g->all_counts[i];
+    int rc = b2p_create(&g->ctx[k], &p);
+    if (rc) return rc; /* g_create_err holds the message */
+    g->n = k + 1;
+    first += g->all_counts[i];
+  }
+  return B2P_OK;
 }
 
 int b2p_group_create(b2p_group **out, const b2p_params *base, const int *devices, const int *nchunks,
@@ -860,31 +917,71 @@ int b2p_group_create(b2p_group **out, const b2p_params *base, const int *devices
   g->nbeam = base->nbeam;
   g->nch = base->nch_per_chunk;
   g->nchan_total = base->nchunk * base->nch_per_chunk;
-  int first = 0;
+  g->base = *base;
+  g->ndev = ndev;
+  g->open_integration = 0;
   for (int i = 0; i < ndev; ++i) {
-    if (nchunks[i] == 0) continue;
-    b2p_params p = *base;
-    p.device_id = devices[i];
-    p.nchunk = nchunks[i];
-    p.first_chunk = first;
-    p.nchunk_total = base->nchunk;
-    p.nsplit = 0;
-    p.stage_ndf = 0;
-    const int k = g->n;
-    g->device[k] = devices[i];
-    g->first[k] = first;
-    g->count[k] = nchunks[i];
-    int rc = b2p_create(&g->ctx[k], &p);
-    if (rc) { /* g_create_err holds the message */
-      for (int j = 0; j < k; ++j) b2p_destroy(g->ctx[j]);
-      delete g;
-      return rc;
-    }
-    g->n = k + 1;
-    first += nchunks[i];
+    g->all_devices[i] = devices[i];
+    g->all_counts[i] = nchunks[i];
+    g->share[i] = (double)nchunks[i] / (double)total;
+  }
+  int rc = group_build(g);
+  if (rc) {
+    for (int j = 0; j < g->n; ++j) b2p_destroy(g->ctx[j]);
+    delete g;
+    return rc;
   }
   g->tmp.resize((size_t)g->nbeam * g->nchan_total);
   *out = g;
+  return B2P_OK;
+}
+
+/*
+ * Move chunks between the GPUs so that their host links finish together: the H2D time of each
+ * shard's last host call (CUDA events on its copy stream) gives the rate its link really
+ * delivered with all links busy — links behind one host bridge slow each other down, which no
+ * solo probe sees.  Only between integrations.  Returns 1 in *changed when the split moved.
+ */
+int b2p_group_rebalance(b2p_group *g, int *changed)
+{
+  if (!g) return B2P_EINVAL;
+  if (changed) *changed = 0;
+  if (g->open_integration) {
+    snprintf(g->err, sizeof(g->err), "b2p_group_rebalance: an integration is open");
+    return B2P_ESTATE;
+  }
+  double rate[B2P_MAX_GROUP], sum_rate = 0.0, sum_share = 0.0;
+  int k = 0;
+  for (int i = 0; i < g->ndev; ++i) {
+    rate[i] = 0.0;
+    if (g->all_counts[i] == 0) continue;
+    double ms = 0.0;
+    int rc = b2p_last_h2d_ms(g->ctx[k], &ms);
+    if (rc) return group_fail(g, k, rc);
+    rate[i] = ms > 0.0 ? (double)g->all_counts[i] / ms : 0.0;
+    sum_rate += rate[i];
+    sum_share += g->share[i];
+    ++k;
+  }
+  if (sum_rate <= 0.0) return B2P_OK;
+  /* damped: half way from the present shares to the measured rates (shares of unused GPUs stay 0) */
+  double target[B2P_MAX_GROUP];
+  for (int i = 0; i < g->ndev; ++i) {
+    target[i] = g->all_counts[i] ? 0.5 * g->share[i] / sum_share + 0.5 * rate[i] / sum_rate : 0.0;
+    g->share[i] = target[i];
+  }
+  int counts[B2P_MAX_GROUP];
+  if (b2p_split_chunks(target, g->ndev, g->base.nchunk, counts) != B2P_OK) return B2P_EINVAL;
+  bool same = true;
+  for (int i = 0; i < g->ndev; ++i) same = same && counts[i] == g->all_counts[i];
+  if (same) return B2P_OK;
+  for (int i = 0; i < g->ndev; ++i) g->all_counts[i] = counts[i];
+  int rc = group_build(g);
+  if (rc) {
+    snprintf(g->err, sizeof(g->err), "b2p_group_rebalance: %s", b2p_last_error(NULL));
+    return rc;
+  }
+  if (changed) *changed = 1;
   return B2P_OK;
 }
 
@@ -928,6 +1025,7 @@ int b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t n
     int rc = b2p_wait_input(g->ctx[i]);
     if (rc) return group_fail(g, i, rc);
   }
+  if (ndf) g->open_integration = 1;
   return B2P_OK;
 }
 
@@ -943,6 +1041,7 @@ int b2p_group_integrate_host(b2p_group *g, const void *const *hptrs, uint64_t nd
     if (rc) return group_fail(g, i, rc);
     group_scatter(g, i, g->tmp.data(), out_host);
   }
+  g->open_integration = 0;
   return B2P_OK;
 }
 
@@ -958,6 +1057,7 @@ int b2p_group_finish(b2p_group *g, float *out_host)
     if (rc) return group_fail(g, i, rc);
     group_scatter(g, i, g->tmp.data(), out_host);
   }
+  g->open_integration = 0;
   return B2P_OK;
 }
 
@@ -968,6 +1068,7 @@ int b2p_group_reset(b2p_group *g)
     int rc = b2p_reset(g->ctx[i]);
     if (rc) return group_fail(g, i, rc);
   }
+  g->open_integration = 0;
   return B2P_OK;
 }
 

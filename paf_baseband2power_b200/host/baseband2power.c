@@ -246,6 +246,19 @@ int do_baseband2power(conf_t *conf)
         }
         ipcio_close_block_write(conf->hdu_out->data_block, conf->rbufsz_out);
         conf->nblocks_out++;
+        if (conf->grp && conf->nblocks_out <= 8) {
+          /* the first integrations tune the chunk split to what the links deliver together */
+          int moved = 0;
+          if (b2p_group_rebalance(conf->grp, &moved) == B2P_OK && moved && conf->log) {
+            char txt[256] = "";
+            for (int i = 0, n = b2p_group_size(conf->grp); i < n; ++i) {
+              int dev = 0, first = 0, cnt = 0;
+              b2p_group_shard(conf->grp, i, &dev, &first, &cnt);
+              snprintf(txt + strlen(txt), sizeof(txt) - strlen(txt), " gpu%d:%d", dev, cnt);
+            }
+            multilog(conf->log, LOG_INFO, "rebalanced chunks per gpu:%s\n", txt);
+          }
+        }
       }
       done += n;
       in_integration = closes ? 0 : in_integration + n;

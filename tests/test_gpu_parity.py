@@ -530,9 +530,19 @@ def test_shard_group_on_one_gpu(b2p, oracle_mod, counts):
         s = want[b] + want[nbeam - 1 - b]
         assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(s).view(np.uint32)), b
     grp.accumulate_host(pins, ndf)
+    with pytest.raises(b2p.B2pError):
+        grp.rebalance()                               # only between integrations
     out = grp.finish()
     for b in range(nbeam):
         assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(want[b]).view(np.uint32)), b
+    # measured rebalancing moves chunks between shards; whatever split it lands on, the
+    # spectrum stays the oracle's
+    for _ in range(4):
+        grp.rebalance()
+        assert sum(n for _, _, n in grp.shards) == 48
+        out = grp.integrate_host(pins, ndf)
+        for b in range(nbeam):
+            assert np.array_equal(out[b].view(np.uint32), oracle_mod.finish(want[b]).view(np.uint32)), b
     grp.close()
     for p in pins:
         p.free()
