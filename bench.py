@@ -864,7 +864,7 @@ def _ring_leg(R):
         # the single-process form of channel-group sharding, through the same rings
         try:
             keys = ring_keys_for_beam(world, 0x1B200 + salt, 0x1B2A0 + salt, 0x100)
-            res = mod.run(ndf=ndf_blk, nbufs=nbufs, nblocks=max(8, args.ring_blocks // 2) * per_int,
+            res = mod.run(ndf=ndf_blk, nbufs=nbufs, nblocks=args.ring_blocks * per_int,
                           gpu=",".join(str(x) for x in R.gpu_map), kernel=args.kernel, keys=keys,
                           ndf_integration=ndf if per_int > 1 else 0, producer_threads=R.vcpus, seed=99)
             res.pop("_spectra", None)

@@ -950,7 +950,7 @@ int b2p_group_rebalance(b2p_group *g, int *changed)
     snprintf(g->err, sizeof(g->err), "b2p_group_rebalance: an integration is open");
     return B2P_ESTATE;
   }
-  double rate[B2P_MAX_GROUP], sum_rate = 0.0, sum_share = 0.0;
+  double rate[B2P_MAX_GROUP], sum_rate = 0.0, sum_share = 0.0, ms_min = 1e300, ms_max = 0.0;
   int k = 0;
   for (int i = 0; i < g->ndev; ++i) {
     rate[i] = 0.0;
@@ -961,9 +961,12 @@ int b2p_group_rebalance(b2p_group *g, int *changed)
     rate[i] = ms > 0.0 ? (double)g->all_counts[i] / ms : 0.0;
     sum_rate += rate[i];
     sum_share += g->share[i];
+    if (ms < ms_min) ms_min = ms;
+    if (ms > ms_max) ms_max = ms;
     ++k;
   }
   if (sum_rate <= 0.0) return B2P_OK;
+  if (ms_max <= 1.04 * ms_min) return B2P_OK; /* the links already finish together */
   /* damped: half way from the present shares to the measured rates (shares of unused GPUs stay 0) */
   double target[B2P_MAX_GROUP];
   for (int i = 0; i < g->ndev; ++i) {

@@ -11,8 +11,7 @@ run() { # n port extra...
 }
 run 8 29521 n8
 run 4 29522 n4_spread
-run 4 29523 n4_identity --placement identity --no-ring --no-live
-python bench.py --impl reference > $out/${tag}_ref.json 2> $out/${tag}_ref.err
+python -m pytest tests/test_gpu_parity.py tests/test_host_ring.py -m gpu -x -q -k "shard or gpu_list or group" 2>&1 | tail -3
 python -  <<'PY'
 import json,glob,sys
 tag=sys.argv[1] if len(sys.argv)>1 else ''
