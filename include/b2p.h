@@ -149,7 +149,9 @@ int b2p_integrate_host(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf, flo
  * kernels and returns at once (finish != 0: the last piece closes the integration and the
  * spectrum's D2H is queued; ndf == 0 with finish: close only); b2p_wait_input returns when
  * the host blocks have been read (the ring block may be released); b2p_wait_output returns
- * the spectrum of the integration closed last.
+ * the spectrum of the OLDEST finished integration not yet collected — up to 4 may be queued,
+ * so a stage can issue the next ring block before it collects the previous spectrum and the
+ * host link never idles between blocks.
  */
 int b2p_accumulate_host_async(b2p_ctx *ctx, const void *const *hptrs, uint64_t ndf, int finish);
 int b2p_wait_input(b2p_ctx *ctx);
@@ -221,6 +223,10 @@ void b2p_group_destroy(b2p_group *g);
 int  b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf);
 int  b2p_group_integrate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, float *out_host);
 int  b2p_group_finish(b2p_group *g, float *out_host);
+/* the asynchronous trio, as for a single context (b2p_accumulate_host_async & co.) */
+int  b2p_group_issue_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, int finish);
+int  b2p_group_wait_input(b2p_group *g);
+int  b2p_group_wait_output(b2p_group *g, float *out_host);
 int  b2p_group_reset(b2p_group *g);
 /* Between integrations: move chunks towards the GPUs whose links delivered more during the
    last host call (H2D time per shard, CUDA events), half way per call.  *changed = 1 when the

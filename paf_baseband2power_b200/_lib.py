@@ -70,6 +70,9 @@ SYMBOLS = {
     "b2p_group_accumulate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64]),
     "b2p_group_integrate_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p]),
     "b2p_group_finish": (c_int, [c_void_p, c_void_p]),
+    "b2p_group_issue_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_int]),
+    "b2p_group_wait_input": (c_int, [c_void_p]),
+    "b2p_group_wait_output": (c_int, [c_void_p, c_void_p]),
     "b2p_group_reset": (c_int, [c_void_p]),
     "b2p_group_rebalance": (c_int, [c_void_p, POINTER(c_int)]),
     "b2p_group_size": (c_int, [c_void_p]),

@@ -21,6 +21,7 @@
 
 #define B2P_MAX_STAGE_BUFS 8
 #define B2P_NTICKETS 4096
+#define B2P_OUT_DEPTH 4 /* finished integrations that may wait to be collected (b2p_wait_output) */
 
 struct b2p_ctx {
   b2p_params p;
@@ -40,8 +41,10 @@ struct b2p_ctx {
   cudaStream_t compute, copy;
   void *acc;
   void *partials;
-  float *out_dev;
-  float *out_pinned;
+  float *out_dev;    /* [B2P_OUT_DEPTH][nbeam][nchan] */
+  float *out_pinned; /* [B2P_OUT_DEPTH][nbeam][nchan] */
+  cudaEvent_t out_ready[B2P_OUT_DEPTH];
+  uint64_t out_head, out_tail; /* spectra queued / collected over the context's life */
   unsigned int *colcnt; /* per (launch beam, column) arrival counters; zero between launches */
   /* ticket counters of the persistent (TMA) kernel: a ring, one per fused launch in flight;
      a launch leaves its counter at zero (the last draw past the end resets it) */
@@ -52,7 +55,6 @@ struct b2p_ctx {
   void *stage[B2P_MAX_STAGE_BUFS];
   cudaEvent_t copied[B2P_MAX_STAGE_BUFS], consumed[B2P_MAX_STAGE_BUFS];
   uint64_t pieces; /* pieces issued so far over the context's life */
-  int out_queued;  /* a D2H of the spectrum is queued on the compute stream */
   cudaEvent_t h2d_begin, h2d_end; /* around the H2D copies of the last host call (copy stream) */
   int h2d_timed;
   /* per-launch timing */
@@ -226,7 +228,8 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   c->acc_elem = 8;
   c->err[0] = 0;
   c->pieces = 0;
-  c->out_queued = 0;
+  c->out_head = c->out_tail = 0;
+  for (int i = 0; i < B2P_OUT_DEPTH; ++i) c->out_ready[i] = NULL;
   c->timing = 0;
   c->ev_used = 0;
   c->launches = 0;
@@ -273,12 +276,13 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(cudaMalloc(&c->acc, nacc * c->acc_elem));
   CKC(cudaMemset(c->acc, 0, nacc * c->acc_elem));
   CKC(cudaMalloc(&c->partials, nacc * (size_t)c->nsplit * c->acc_elem));
-  CKC(cudaMalloc((void **)&c->out_dev, nacc * sizeof(float)));
+  CKC(cudaMalloc((void **)&c->out_dev, B2P_OUT_DEPTH * nacc * sizeof(float)));
+  for (int i = 0; i < B2P_OUT_DEPTH; ++i) CKC(cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming));
   CKC(cudaMalloc((void **)&c->tickets, B2P_NTICKETS * sizeof(unsigned int)));
   CKC(cudaMemset(c->tickets, 0, B2P_NTICKETS * sizeof(unsigned int)));
   CKC(cudaMalloc((void **)&c->colcnt, ncnt * sizeof(unsigned int)));
   CKC(cudaMemset(c->colcnt, 0, ncnt * sizeof(unsigned int)));
-  CKC(cudaHostAlloc((void **)&c->out_pinned, nacc * sizeof(float), cudaHostAllocDefault));
+  CKC(cudaHostAlloc((void **)&c->out_pinned, B2P_OUT_DEPTH * nacc * sizeof(float), cudaHostAllocDefault));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = c;
@@ -299,6 +303,8 @@ void b2p_destroy(b2p_ctx *c)
   }
   for (size_t i = 0; i < c->ev_pool.size(); ++i) cudaEventDestroy(c->ev_pool[i]);
   if (c->xev) cudaEventDestroy(c->xev);
+  for (int i = 0; i < B2P_OUT_DEPTH; ++i)
+    if (c->out_ready[i]) cudaEventDestroy(c->out_ready[i]);
   if (c->h2d_begin) cudaEventDestroy(c->h2d_begin);
   if (c->h2d_end) cudaEventDestroy(c->h2d_end);
   if (c->acc) cudaFree(c->acc);
@@ -488,9 +494,16 @@ static int host_issue(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int fi
       if (!hptrs[b]) FAIL(c, B2P_EINVAL, "b2p_accumulate_host: NULL beam pointer");
   }
   CK(c, cudaSetDevice(c->p.device_id));
+  const size_t nacc = (size_t)c->p.nbeam * c->nchan;
+  float *out_slot = NULL;
+  if (finish) {
+    if (c->out_head - c->out_tail >= B2P_OUT_DEPTH)
+      FAIL(c, B2P_ESTATE, "too many finished integrations wait to be collected (b2p_wait_output)");
+    out_slot = c->out_dev + (c->out_head % B2P_OUT_DEPTH) * nacc;
+  }
   if (ndf == 0) {
     if (!finish) return B2P_OK;
-    int rc0 = b2p_finish_device(c, c->out_dev, c->compute);
+    int rc0 = b2p_finish_device(c, out_slot, c->compute);
     if (rc0) return rc0;
   }
   int rc = ensure_staging(c);
@@ -514,7 +527,7 @@ static int host_issue(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int fi
       CK(c, cudaStreamWaitEvent(c->compute, c->copied[buf], 0));
       const void *ptr = c->stage[buf];
       const int fin = finish && f0 + n == ndf;
-      rc = launch_fused(c, &ptr, &b, 1, n, c->frame_bytes, c->kernel, c->compute, fin, c->out_dev);
+      rc = launch_fused(c, &ptr, &b, 1, n, c->frame_bytes, c->kernel, c->compute, fin, out_slot);
       if (rc) return rc;
       CK(c, cudaEventRecord(c->consumed[buf], c->compute));
       c->pieces++;
@@ -525,9 +538,11 @@ static int host_issue(b2p_ctx *c, const void *const *hptrs, uint64_t ndf, int fi
     c->h2d_timed = 1;
   }
   if (finish) {
-    const size_t bytes = (size_t)c->p.nbeam * c->nchan * sizeof(float);
-    CK(c, cudaMemcpyAsync(c->out_pinned, c->out_dev, bytes, cudaMemcpyDeviceToHost, c->compute));
-    c->out_queued = 1;
+    const int slot = (int)(c->out_head % B2P_OUT_DEPTH);
+    CK(c, cudaMemcpyAsync(c->out_pinned + slot * nacc, out_slot, nacc * sizeof(float), cudaMemcpyDeviceToHost,
+                          c->compute));
+    CK(c, cudaEventRecord(c->out_ready[slot], c->compute));
+    c->out_head++;
   }
   return B2P_OK;
 }
@@ -563,11 +578,13 @@ int b2p_wait_output(b2p_ctx *c, float *out_host)
 {
   if (!c) return B2P_EINVAL;
   if (!out_host) FAIL(c, B2P_EINVAL, "b2p_wait_output: NULL output");
-  if (!c->out_queued) FAIL(c, B2P_ESTATE, "b2p_wait_output: no finished integration is queued");
+  if (c->out_head == c->out_tail) FAIL(c, B2P_ESTATE, "b2p_wait_output: no finished integration is queued");
   CK(c, cudaSetDevice(c->p.device_id));
-  CK(c, cudaStreamSynchronize(c->compute));
-  memcpy(out_host, c->out_pinned, (size_t)c->p.nbeam * c->nchan * sizeof(float));
-  c->out_queued = 0;
+  const size_t nacc = (size_t)c->p.nbeam * c->nchan;
+  const int slot = (int)(c->out_tail % B2P_OUT_DEPTH);
+  CK(c, cudaEventSynchronize(c->out_ready[slot])); /* the oldest one; later work keeps running */
+  memcpy(out_host, c->out_pinned + slot * nacc, nacc * sizeof(float));
+  c->out_tail++;
   return B2P_OK;
 }
 
@@ -635,14 +652,11 @@ int b2p_finish(b2p_ctx *c, float *out_host)
 {
   if (!c) return B2P_EINVAL;
   if (!out_host) FAIL(c, B2P_EINVAL, "b2p_finish: NULL output");
-  int rc = b2p_finish_device(c, c->out_dev, c->compute);
+  if (c->out_head != c->out_tail)
+    FAIL(c, B2P_ESTATE, "b2p_finish: collect the queued integrations first (b2p_wait_output)");
+  int rc = host_issue(c, NULL, 0, 1); /* finish kernel + D2H into the output queue */
   if (rc) return rc;
-  const size_t bytes = (size_t)c->p.nbeam * c->nchan * sizeof(float);
-  CK(c, cudaMemcpyAsync(c->out_pinned, c->out_dev, bytes, cudaMemcpyDeviceToHost, c->compute));
-  CK(c, cudaStreamSynchronize(c->compute));
-  memcpy(out_host, c->out_pinned, bytes);
-  c->out_queued = 0;
-  return B2P_OK;
+  return b2p_wait_output(c, out_host);
 }
 
 /* wait for everything the context has launched, wherever it launched it */
@@ -675,7 +689,7 @@ int b2p_reset(b2p_ctx *c)
   /* nothing else to put right: every launch leaves its counters (columns, TMA ticket) at zero */
   CK(c, cudaMemsetAsync(c->acc, 0, (size_t)c->p.nbeam * c->nchan * c->acc_elem, c->compute));
   CK(c, cudaStreamSynchronize(c->compute));
-  c->out_queued = 0;
+  c->out_tail = c->out_head; /* drop spectra nobody collected */
   return B2P_OK;
 }
 
@@ -950,6 +964,11 @@ int b2p_group_rebalance(b2p_group *g, int *changed)
     snprintf(g->err, sizeof(g->err), "b2p_group_rebalance: an integration is open");
     return B2P_ESTATE;
   }
+  for (int i = 0; i < g->n; ++i)
+    if (g->ctx[i]->out_head != g->ctx[i]->out_tail) {
+      snprintf(g->err, sizeof(g->err), "b2p_group_rebalance: finished integrations wait to be collected");
+      return B2P_ESTATE;
+    }
   double rate[B2P_MAX_GROUP], sum_rate = 0.0, sum_share = 0.0, ms_min = 1e300, ms_max = 0.0;
   int k = 0;
   for (int i = 0; i < g->ndev; ++i) {
@@ -1016,52 +1035,57 @@ static void group_scatter(const b2p_group *g, int i, const float *part, float *o
            (size_t)w * sizeof(float));
 }
 
-int b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf)
+/* queue every GPU's copies and kernels (one host thread keeps all links busy); nothing waits */
+int b2p_group_issue_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, int finish)
 {
   if (!g) return B2P_EINVAL;
-  /* queue every GPU's copies and kernels first, wait afterwards: one host thread, all links busy */
   for (int i = 0; i < g->n; ++i) {
-    int rc = b2p_accumulate_host_async(g->ctx[i], hptrs, ndf, 0);
+    int rc = b2p_accumulate_host_async(g->ctx[i], hptrs, ndf, finish);
     if (rc) return group_fail(g, i, rc);
   }
+  g->open_integration = finish ? 0 : (ndf ? 1 : g->open_integration);
+  return B2P_OK;
+}
+
+int b2p_group_wait_input(b2p_group *g)
+{
+  if (!g) return B2P_EINVAL;
   for (int i = 0; i < g->n; ++i) {
     int rc = b2p_wait_input(g->ctx[i]);
     if (rc) return group_fail(g, i, rc);
   }
-  if (ndf) g->open_integration = 1;
   return B2P_OK;
+}
+
+int b2p_group_wait_output(b2p_group *g, float *out_host)
+{
+  if (!g || !out_host) return B2P_EINVAL;
+  for (int i = 0; i < g->n; ++i) {
+    int rc = b2p_wait_output(g->ctx[i], g->tmp.data());
+    if (rc) return group_fail(g, i, rc);
+    group_scatter(g, i, g->tmp.data(), out_host);
+  }
+  return B2P_OK;
+}
+
+int b2p_group_accumulate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf)
+{
+  int rc = b2p_group_issue_host(g, hptrs, ndf, 0);
+  return rc ? rc : b2p_group_wait_input(g);
 }
 
 int b2p_group_integrate_host(b2p_group *g, const void *const *hptrs, uint64_t ndf, float *out_host)
 {
   if (!g || !out_host) return B2P_EINVAL;
-  for (int i = 0; i < g->n; ++i) {
-    int rc = b2p_accumulate_host_async(g->ctx[i], hptrs, ndf, 1);
-    if (rc) return group_fail(g, i, rc);
-  }
-  for (int i = 0; i < g->n; ++i) {
-    int rc = b2p_wait_output(g->ctx[i], g->tmp.data());
-    if (rc) return group_fail(g, i, rc);
-    group_scatter(g, i, g->tmp.data(), out_host);
-  }
-  g->open_integration = 0;
-  return B2P_OK;
+  int rc = b2p_group_issue_host(g, hptrs, ndf, 1);
+  return rc ? rc : b2p_group_wait_output(g, out_host);
 }
 
 int b2p_group_finish(b2p_group *g, float *out_host)
 {
   if (!g || !out_host) return B2P_EINVAL;
-  for (int i = 0; i < g->n; ++i) {
-    int rc = b2p_accumulate_host_async(g->ctx[i], NULL, 0, 1); /* ndf 0: finish only */
-    if (rc) return group_fail(g, i, rc);
-  }
-  for (int i = 0; i < g->n; ++i) {
-    int rc = b2p_wait_output(g->ctx[i], g->tmp.data());
-    if (rc) return group_fail(g, i, rc);
-    group_scatter(g, i, g->tmp.data(), out_host);
-  }
-  g->open_integration = 0;
-  return B2P_OK;
+  int rc = b2p_group_issue_host(g, NULL, 0, 1); /* ndf 0: finish only */
+  return rc ? rc : b2p_group_wait_output(g, out_host);
 }
 
 int b2p_group_reset(b2p_group *g)

@@ -177,6 +177,32 @@ static int rewrite_header(conf_t *conf, char *hdr)
   return rc;
 }
 
+/* Write the `n` oldest finished spectra into output ring blocks (each b2p_wait_output returns
+   the oldest integration not yet collected); in group mode the first integrations also tune
+   the chunk split to what the links deliver together. */
+static int collect_spectra(conf_t *conf, unsigned *due, unsigned n)
+{
+  for (; n > 0 && *due > 0; --n) {
+    uint64_t out_id = 0;
+    char *out = ipcio_open_block_write(conf->hdu_out->data_block, &out_id);
+    if (!out) {
+      STAGE_ERR(conf, "Can not open an output block\n");
+      return EXIT_FAILURE;
+    }
+    const int rc = conf->grp ? b2p_group_wait_output(conf->grp, (float *)out)
+                             : b2p_wait_output(conf->ctx, (float *)out);
+    if (rc != B2P_OK) {
+      STAGE_ERR(conf, "collecting a spectrum failed: %s\n",
+                conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
+      return EXIT_FAILURE;
+    }
+    ipcio_close_block_write(conf->hdu_out->data_block, conf->rbufsz_out);
+    conf->nblocks_out++;
+    *due -= 1;
+  }
+  return EXIT_SUCCESS;
+}
+
 int do_baseband2power(conf_t *conf)
 {
   /* ---- header: in -> out ---- */
@@ -205,8 +231,17 @@ int do_baseband2power(conf_t *conf)
   ipcbuf_enable_sod((ipcbuf_t *)conf->hdu_out->data_block, 0, 0);
 
   /* ---- data ---- */
+  /*
+   * One block ahead: the copies and kernels of a block are queued without waiting, the ring
+   * block goes back as soon as its bytes have left the host, and the spectrum of an integration
+   * is collected only after the NEXT block has been queued (when one is already waiting in the
+   * ring) — so the host links never idle between blocks.  When the ring is empty (a live stream
+   * at 1x) the spectra are written out at once.
+   */
   const uint64_t frame_bytes = (uint64_t)conf->nchunk * PKT_BYTES(conf);
+  ipcbuf_t *db_in = (ipcbuf_t *)conf->hdu_in->data_block;
   uint64_t in_integration = 0;
+  unsigned due = 0; /* integrations closed on the GPU whose spectra are not in the output ring yet */
   for (;;) {
     uint64_t bytes = 0, block_id = 0;
     char *blk = ipcio_open_block_read(conf->hdu_in->data_block, &bytes, &block_id);
@@ -219,54 +254,52 @@ int do_baseband2power(conf_t *conf)
       if (n > ndf - done) n = ndf - done;
       const void *ptr = blk + done * frame_bytes;
       const int closes = in_integration + n == conf->ndf_integration;
-      if (!closes) {
-        const int rc = conf->grp ? b2p_group_accumulate_host(conf->grp, &ptr, n)
-                                 : b2p_accumulate_host(conf->ctx, &ptr, n);
-        if (rc != B2P_OK) {
-          STAGE_ERR(conf, "b2p_accumulate_host failed: %s\n",
-                    conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
-          return EXIT_FAILURE;
-        }
-      } else {
-        /* these frames complete an integration: the kernel of the last staging piece emits
-           the spectrum itself (one launch per piece, no separate finish), straight into
-           the output ring block */
-        uint64_t out_id = 0;
-        char *out = ipcio_open_block_write(conf->hdu_out->data_block, &out_id);
-        if (!out) {
-          STAGE_ERR(conf, "Can not open an output block\n");
-          return EXIT_FAILURE;
-        }
-        const int rc = conf->grp ? b2p_group_integrate_host(conf->grp, &ptr, n, (float *)out)
-                                 : b2p_integrate_host(conf->ctx, &ptr, n, (float *)out);
-        if (rc != B2P_OK) {
-          STAGE_ERR(conf, "b2p_integrate_host failed: %s\n",
-                    conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
-          return EXIT_FAILURE;
-        }
-        ipcio_close_block_write(conf->hdu_out->data_block, conf->rbufsz_out);
-        conf->nblocks_out++;
-        if (conf->grp && conf->nblocks_out <= 8) {
-          /* the first integrations tune the chunk split to what the links deliver together */
-          int moved = 0;
-          if (b2p_group_rebalance(conf->grp, &moved) == B2P_OK && moved && conf->log) {
-            char txt[256] = "";
-            for (int i = 0, n = b2p_group_size(conf->grp); i < n; ++i) {
-              int dev = 0, first = 0, cnt = 0;
-              b2p_group_shard(conf->grp, i, &dev, &first, &cnt);
-              snprintf(txt + strlen(txt), sizeof(txt) - strlen(txt), " gpu%d:%d", dev, cnt);
-            }
-            multilog(conf->log, LOG_INFO, "rebalanced chunks per gpu:%s\n", txt);
-          }
-        }
+      if (closes && due >= 3 && collect_spectra(conf, &due, 1) != EXIT_SUCCESS) return EXIT_FAILURE;
+      /* when these frames complete an integration, the kernel of the last staging piece emits
+         the spectrum itself (one launch per piece, no separate finish) */
+      const int rc = conf->grp ? b2p_group_issue_host(conf->grp, &ptr, n, closes)
+                               : b2p_accumulate_host_async(conf->ctx, &ptr, n, closes);
+      if (rc != B2P_OK) {
+        STAGE_ERR(conf, "queueing a block failed: %s\n",
+                  conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
+        return EXIT_FAILURE;
       }
+      if (closes) due++;
       done += n;
       in_integration = closes ? 0 : in_integration + n;
     }
+    /* spectra of earlier blocks: their kernels ran while this block was being queued */
+    const unsigned just_queued = (in_integration == 0 && ndf) ? 1 : 0;
+    if (due > just_queued && collect_spectra(conf, &due, due - just_queued) != EXIT_SUCCESS) return EXIT_FAILURE;
+    if ((conf->grp ? b2p_group_wait_input(conf->grp) : b2p_wait_input(conf->ctx)) != B2P_OK) {
+      STAGE_ERR(conf, "waiting for the H2D copies failed: %s\n",
+                conf->grp ? b2p_group_last_error(conf->grp) : b2p_last_error(conf->ctx));
+      return EXIT_FAILURE;
+    }
     ipcio_close_block_read(conf->hdu_in->data_block, bytes);
     conf->nblocks_in++;
+    /* nothing waiting in the ring: do not sit on a finished spectrum until the next block comes.
+       Several GPUs: the first integrations are not run ahead either — each one's measured copy
+       times move chunks towards the faster links (b2p_group_rebalance) before the next starts. */
+    const int tuning = conf->grp && conf->nblocks_out + due <= 8;
+    if (due && (tuning || ipcbuf_get_write_count(db_in) <= ipcbuf_get_read_count(db_in)) &&
+        collect_spectra(conf, &due, due) != EXIT_SUCCESS)
+      return EXIT_FAILURE;
+    if (tuning && due == 0 && in_integration == 0) {
+      int moved = 0;
+      if (b2p_group_rebalance(conf->grp, &moved) == B2P_OK && moved && conf->log) {
+        char txt[256] = "";
+        for (int i = 0, n = b2p_group_size(conf->grp); i < n; ++i) {
+          int dev = 0, first = 0, cnt = 0;
+          b2p_group_shard(conf->grp, i, &dev, &first, &cnt);
+          snprintf(txt + strlen(txt), sizeof(txt) - strlen(txt), " gpu%d:%d", dev, cnt);
+        }
+        multilog(conf->log, LOG_INFO, "rebalanced chunks per gpu:%s\n", txt);
+      }
+    }
     conf->seconds_busy += now_s() - t0;
   }
+  if (due && collect_spectra(conf, &due, due) != EXIT_SUCCESS) return EXIT_FAILURE;
   if (in_integration) { /* an incomplete integration has the wrong scale: do not emit it */
     conf->nframes_dropped += in_integration;
     if (conf->grp)

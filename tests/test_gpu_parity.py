@@ -679,3 +679,34 @@ def test_cuda_graph_of_single_launch_integration(b2p, oracle_mod, kernel):
         for k in range(2):
             assert np.array_equal(res[k].view(np.uint32), want[i].view(np.uint32)), (kernel, rep, k)
     st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_output_queue_runs_integrations_ahead(b2p, oracle_mod, kernel):
+    """Up to 4 finished integrations may wait to be collected: a stage queues the next ring block
+    before it collects the previous spectrum.  Spectra come back oldest first."""
+    ndf = 48
+    blocks = [oracle_mod.synth_fill(ndf, seed=1100 + i, mode=1) for i in range(4)]
+    pins = [b2p.PinnedBuffer(b.nbytes) for b in blocks]
+    for p, b in zip(pins, blocks):
+        p.array[:] = b
+    want = [oracle_mod.finish(oracle_mod.accumulate_omp(b)) for b in blocks]
+    st = b2p.Baseband2Power(kernel=kernel, stage_ndf=16)
+    for p in pins:
+        st.accumulate_host_async([p], ndf, finish=True)
+    with pytest.raises(b2p.B2pError):
+        st.accumulate_host_async([pins[0]], ndf, finish=True)     # a fifth: collect first
+    with pytest.raises(b2p.B2pError):
+        st.finish()                                               # not while spectra are queued
+    st.reset()                                                    # drops the frames of the refused call and the queue
+    for rep in range(2):                                          # two ahead, steady state
+        st.accumulate_host_async([pins[0]], ndf, finish=True)
+        for i in range(1, 4):
+            st.accumulate_host_async([pins[i]], ndf, finish=True)
+            st.wait_input()
+            got = st.wait_output()[0]                             # spectrum of block i-1
+            assert np.array_equal(got.view(np.uint32), want[i - 1].view(np.uint32)), (rep, i)
+        assert np.array_equal(st.wait_output()[0].view(np.uint32), want[3].view(np.uint32))
+    st.close()
+    for p in pins:
+        p.free()
