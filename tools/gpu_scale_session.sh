@@ -10,8 +10,10 @@ run() { # n port extra...
   echo "$name rc=$? $((SECONDS - t0)) s wall"
 }
 run 8 29521 n8
-run 4 29522 n4_spread
-python -m pytest tests/test_gpu_parity.py tests/test_host_ring.py -m gpu -x -q -k "shard or gpu_list or group" 2>&1 | tail -3
+run 4 29522 n4
+run 2 29523 n2
+python bench.py --impl reference > $out/${tag}_ref.json 2> $out/${tag}_ref.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 python -  <<'PY'
 import json,glob,sys
 tag=sys.argv[1] if len(sys.argv)>1 else ''
