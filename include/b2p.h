@@ -79,6 +79,8 @@ typedef struct b2p_params {
      0 of the full stream — the ring block as ipcio_open_block_read returns it. */
   int first_chunk;
   int nchunk_total;
+  int resizable;        /* 1: size the buffers for any chunk range of nchunk_total, so that
+                           b2p_set_chunk_range can move the range later without reallocating */
 } b2p_params;
 
 /* Fill *p with the reference pipeline's defaults (one beam, exact mode, scale 1). */
@@ -177,6 +179,10 @@ int b2p_accumulate_host_mapped(b2p_ctx *ctx, const void *const *hptrs, uint64_t 
  */
 int b2p_finish(b2p_ctx *ctx, float *out_host);
 int b2p_finish_device(b2p_ctx *ctx, float *out_dev, void *stream);
+
+/* Move a resizable context to chunks [first_chunk, first_chunk + nchunk) — between
+   integrations only (the accumulators are cleared); no allocation, a few microseconds. */
+int b2p_set_chunk_range(b2p_ctx *ctx, int first_chunk, int nchunk);
 
 /* Copy the exact uint64 sums [nbeam*nchan] to the host without resetting (exact mode). */
 int b2p_read_sums(b2p_ctx *ctx, uint64_t *sums_host);

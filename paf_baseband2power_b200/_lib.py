@@ -28,7 +28,7 @@ class B2pParams(Structure):
         ("device_id", c_int), ("nchunk", c_int), ("nch_per_chunk", c_int), ("nsamp_df", c_int),
         ("big_endian", c_int), ("scale", c_float), ("mode", c_int), ("nbeam", c_int),
         ("kernel", c_int), ("nsplit", c_int), ("stage_ndf", c_uint64), ("nstage_bufs", c_int),
-        ("first_chunk", c_int), ("nchunk_total", c_int),
+        ("first_chunk", c_int), ("nchunk_total", c_int), ("resizable", c_int),
     ]
 
 
@@ -49,6 +49,7 @@ SYMBOLS = {
     "b2p_accumulate_host_mapped": (c_int, [c_void_p, POINTER(c_void_p), c_uint64]),
     "b2p_finish": (c_int, [c_void_p, c_void_p]),
     "b2p_finish_device": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "b2p_set_chunk_range": (c_int, [c_void_p, c_int, c_int]),
     "b2p_read_sums": (c_int, [c_void_p, c_void_p]),
     "b2p_reset": (c_int, [c_void_p]),
     "b2p_nchan": (c_int, [c_void_p]),

@@ -148,7 +148,7 @@ class Baseband2Power:
     def __init__(self, device_id: int = 0, nbeam: int = 1, nchunk: int = 48, nch_per_chunk: int = 7,
                  nsamp_df: int = 128, big_endian: bool = True, scale: float = 1.0,
                  mode: str = "exact", kernel: str = "auto", nsplit: int = 0, stage_ndf: int = 0,
-                 nstage_bufs: int = 0, first_chunk: int = 0, nchunk_total: int = 0):
+                 nstage_bufs: int = 0, first_chunk: int = 0, nchunk_total: int = 0, resizable: bool = False):
         self._lib = _lib.load()
         p = B2pParams()
         self._lib.b2p_default_params(byref(p))
@@ -157,7 +157,7 @@ class Baseband2Power:
         p.big_endian, p.scale = int(big_endian), scale
         p.mode, p.kernel = _MODES[mode], _KERNELS[kernel]
         p.nsplit, p.stage_ndf, p.nstage_bufs = nsplit, stage_ndf, nstage_bufs
-        p.first_chunk, p.nchunk_total = first_chunk, nchunk_total
+        p.first_chunk, p.nchunk_total, p.resizable = first_chunk, nchunk_total, int(resizable)
         ctx = c_void_p()
         _check(self._lib.b2p_create(byref(ctx), byref(p)))
         self._ctx = ctx
@@ -259,6 +259,12 @@ class Baseband2Power:
 
     def finish_device(self, out_dev, stream: int | None = None):
         _check(self._lib.b2p_finish_device(self._ctx, _dev_ptr(out_dev), stream), self._ctx)
+
+    def set_chunk_range(self, first_chunk: int, nchunk: int):
+        """Move a resizable shard context to another chunk range (between integrations)."""
+        _check(self._lib.b2p_set_chunk_range(self._ctx, first_chunk, nchunk), self._ctx)
+        self.nchan = self._lib.b2p_nchan(self._ctx)
+        self.frame_bytes = self._lib.b2p_frame_bytes(self._ctx)
 
     def read_sums(self) -> np.ndarray:
         out = np.empty((self.nbeam, self.nchan), dtype=np.uint64)

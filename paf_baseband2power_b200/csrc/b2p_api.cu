@@ -34,6 +34,9 @@ struct b2p_ctx {
   int kernel;  /* resolved */
   int nsplit;  /* resolved: splits of a full-length launch */
   int split_base; /* smallest split count that fills whole waves */
+  int cap_nchunk; /* chunks the buffers are sized for (nchunk_total when the range may move) */
+  int cap_nsplit;
+  uint64_t user_stage_ndf; /* stage_ndf as given at creation (0 = derive from the chunk range) */
   int variant; /* tuning variant, B2P_VARIANT env (experiments) */
   int no_early; /* B2P_NO_EARLY=1: never start a fused kernel before its predecessor ends */
   int calib;
@@ -120,6 +123,7 @@ void b2p_default_params(b2p_params *p)
   p->nstage_bufs = 0;
   p->first_chunk = 0;
   p->nchunk_total = 0;
+  p->resizable = 0;
 }
 
 const char *b2p_last_error(const b2p_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
@@ -263,6 +267,17 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(b2p_kernels_configure());
   c->kernel = resolve_kernel(p);
   c->nsplit = resolve_nsplit(p, c->kernel, c->sm_count, &c->split_base);
+  c->user_stage_ndf = p->stage_ndf;
+  c->cap_nchunk = p->resizable ? ntotal : p->nchunk;
+  c->cap_nsplit = c->nsplit;
+  if (p->resizable) /* the chunk range may be moved later: size the scratch for any range */
+    for (int n = 1; n <= ntotal; ++n) {
+      b2p_params q = *p;
+      q.nchunk = n;
+      int base = 0;
+      const int ns = resolve_nsplit(&q, resolve_kernel(&q), c->sm_count, &base);
+      if (ns > c->cap_nsplit) c->cap_nsplit = ns;
+    }
   c->variant = getenv("B2P_VARIANT") ? atoi(getenv("B2P_VARIANT")) : 0;
   c->no_early = getenv("B2P_NO_EARLY") ? atoi(getenv("B2P_NO_EARLY")) : 0;
   c->calib = getenv("B2P_CALIB") ? atoi(getenv("B2P_CALIB")) : 0;
@@ -271,11 +286,11 @@ int b2p_create(b2p_ctx **out, const b2p_params *p)
   CKC(cudaEventCreateWithFlags(&c->xev, cudaEventDisableTiming));
   CKC(cudaEventCreate(&c->h2d_begin));
   CKC(cudaEventCreate(&c->h2d_end));
-  const size_t nacc = (size_t)p->nbeam * c->nchan;
-  const size_t ncnt = (size_t)p->nbeam * p->nchunk;
+  const size_t nacc = (size_t)p->nbeam * c->cap_nchunk * p->nch_per_chunk;
+  const size_t ncnt = (size_t)p->nbeam * c->cap_nchunk;
   CKC(cudaMalloc(&c->acc, nacc * c->acc_elem));
   CKC(cudaMemset(c->acc, 0, nacc * c->acc_elem));
-  CKC(cudaMalloc(&c->partials, nacc * (size_t)c->nsplit * c->acc_elem));
+  CKC(cudaMalloc(&c->partials, nacc * (size_t)c->cap_nsplit * c->acc_elem));
   CKC(cudaMalloc((void **)&c->out_dev, B2P_OUT_DEPTH * nacc * sizeof(float)));
   for (int i = 0; i < B2P_OUT_DEPTH; ++i) CKC(cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming));
   CKC(cudaMalloc((void **)&c->tickets, B2P_NTICKETS * sizeof(unsigned int)));
@@ -468,12 +483,16 @@ static int ensure_staging(b2p_ctx *c)
   int nb = c->p.nstage_bufs > 0 ? c->p.nstage_bufs : 3;
   if (nb < 2) nb = 2;
   if (nb > B2P_MAX_STAGE_BUFS) nb = B2P_MAX_STAGE_BUFS;
-  if (c->p.stage_ndf == 0) {
+  size_t bytes;
+  if (c->user_stage_ndf == 0) {
     /* ~88 MB per piece whatever the shard width: 256 frames of 48 chunks */
     uint64_t n = 256u * (uint64_t)c->p.nchunk_total / (uint64_t)c->p.nchunk;
     c->p.stage_ndf = n ? n : 1;
+    bytes = (size_t)256u * c->p.nchunk_total * c->pkt_bytes;
+    if (bytes < (size_t)c->p.stage_ndf * c->frame_bytes) bytes = (size_t)c->p.stage_ndf * c->frame_bytes;
+  } else {
+    bytes = (size_t)c->user_stage_ndf * c->cap_nchunk * c->pkt_bytes;
   }
-  const size_t bytes = (size_t)c->p.stage_ndf * c->frame_bytes;
   for (int i = 0; i < nb; ++i) {
     CK(c, cudaMalloc(&c->stage[i], bytes));
     CK(c, cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming));
@@ -693,6 +712,34 @@ int b2p_reset(b2p_ctx *c)
   return B2P_OK;
 }
 
+int b2p_set_chunk_range(b2p_ctx *c, int first_chunk, int nchunk)
+{
+  if (!c) return B2P_EINVAL;
+  if (!c->p.resizable) FAIL(c, B2P_ESTATE, "b2p_set_chunk_range: the context was not created resizable");
+  if (nchunk < 1 || first_chunk < 0 || first_chunk + nchunk > c->p.nchunk_total)
+    FAIL(c, B2P_EINVAL, "b2p_set_chunk_range: range exceeds nchunk_total");
+  if (c->out_head != c->out_tail)
+    FAIL(c, B2P_ESTATE, "b2p_set_chunk_range: finished integrations wait to be collected");
+  CK(c, cudaSetDevice(c->p.device_id));
+  int rc = drain(c);
+  if (rc) return rc;
+  c->p.nchunk = nchunk;
+  c->p.first_chunk = first_chunk;
+  c->nchan = nchunk * c->p.nch_per_chunk;
+  c->frame_bytes = (uint64_t)nchunk * c->pkt_bytes;
+  c->src_offset = (uint64_t)first_chunk * c->pkt_bytes;
+  c->nsplit = resolve_nsplit(&c->p, c->kernel, c->sm_count, &c->split_base);
+  if (c->nsplit > c->cap_nsplit) c->nsplit = c->cap_nsplit;
+  if (c->user_stage_ndf == 0) {
+    uint64_t n = 256u * (uint64_t)c->p.nchunk_total / (uint64_t)nchunk;
+    c->p.stage_ndf = n ? n : 1;
+  }
+  /* between integrations the accumulators are zero anyway; their row pitch has changed */
+  CK(c, cudaMemsetAsync(c->acc, 0, (size_t)c->p.nbeam * c->cap_nchunk * c->p.nch_per_chunk * c->acc_elem, c->compute));
+  CK(c, cudaStreamSynchronize(c->compute));
+  return B2P_OK;
+}
+
 int b2p_set_timing(b2p_ctx *c, int enabled)
 {
   if (!c) return B2P_EINVAL;
@@ -899,6 +946,7 @@ static int group_build(b2p_group *g)
     p.nchunk_total = g->base.nchunk;
     p.nsplit = 0;
     p.stage_ndf = 0;
+    p.resizable = 1; /* b2p_group_rebalance moves the range in place */
     const int k = g->n;
     g->device[k] = g->all_devices[i];
     g->first[k] = first;
@@ -994,14 +1042,30 @@ int b2p_group_rebalance(b2p_group *g, int *changed)
   }
   int counts[B2P_MAX_GROUP];
   if (b2p_split_chunks(target, g->ndev, g->base.nchunk, counts) != B2P_OK) return B2P_EINVAL;
+  /* a GPU that takes part keeps at least one chunk (its context stays) */
+  for (int i = 0; i < g->ndev; ++i)
+    if (g->all_counts[i] > 0 && counts[i] == 0) {
+      int big = 0;
+      for (int j = 1; j < g->ndev; ++j)
+        if (counts[j] > counts[big]) big = j;
+      counts[big] -= 1;
+      counts[i] = 1;
+    }
   bool same = true;
   for (int i = 0; i < g->ndev; ++i) same = same && counts[i] == g->all_counts[i];
   if (same) return B2P_OK;
-  for (int i = 0; i < g->ndev; ++i) g->all_counts[i] = counts[i];
-  int rc = group_build(g);
-  if (rc) {
-    snprintf(g->err, sizeof(g->err), "b2p_group_rebalance: %s", b2p_last_error(NULL));
-    return rc;
+  /* move the ranges in place: no allocation, no context rebuilt */
+  int first = 0;
+  k = 0;
+  for (int i = 0; i < g->ndev; ++i) {
+    if (g->all_counts[i] == 0) continue;
+    int rc = b2p_set_chunk_range(g->ctx[k], first, counts[i]);
+    if (rc) return group_fail(g, k, rc);
+    g->first[k] = first;
+    g->count[k] = counts[i];
+    g->all_counts[i] = counts[i];
+    first += counts[i];
+    ++k;
   }
   if (changed) *changed = 1;
   return B2P_OK;

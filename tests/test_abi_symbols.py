@@ -44,7 +44,7 @@ def test_params_struct_matches_header_defaults():
     assert (p.nchunk, p.nch_per_chunk, p.nsamp_df, p.big_endian) == (48, 7, 128, 1)
     assert (p.scale, p.mode, p.nbeam, p.kernel, p.nsplit) == (1.0, 0, 1, 0, 0)
     assert (p.stage_ndf, p.nstage_bufs, p.device_id) == (0, 0, 0)
-    assert (p.first_chunk, p.nchunk_total) == (0, 0)
+    assert (p.first_chunk, p.nchunk_total, p.resizable) == (0, 0, 0)
     # the ctypes mirror and the C struct must agree on the size (a drifted field would shift all)
     assert ctypes.sizeof(_lib.B2pParams) == 64
 

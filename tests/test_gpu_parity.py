@@ -710,3 +710,32 @@ def test_output_queue_runs_integrations_ahead(b2p, oracle_mod, kernel):
     st.close()
     for p in pins:
         p.free()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_resizable_shard_moves_its_chunk_range_in_place(b2p, oracle_mod, kernel):
+    """b2p_set_chunk_range: what b2p_group_rebalance does to follow the measured link rates."""
+    g = oracle_mod.Geometry()
+    ndf = 60
+    block = oracle_mod.synth_fill(ndf, seed=1200, mode=1)
+    want = oracle_mod.finish(oracle_mod.accumulate_omp(block))
+    pin = b2p.PinnedBuffer(block.nbytes)
+    pin.array[:] = block
+    st = b2p.Baseband2Power(kernel=kernel, nchunk=6, first_chunk=0, nchunk_total=48, resizable=True)
+    for first, n in [(0, 6), (6, 1), (7, 41), (0, 48), (47, 1), (10, 13)]:
+        st.set_chunk_range(first, n)
+        assert st.nchan == 7 * n
+        got = st.integrate_host([pin], ndf)[0]
+        assert np.array_equal(got.view(np.uint32), want[7 * first:7 * (first + n)].view(np.uint32)), (first, n)
+        st.accumulate_host_mapped([pin], ndf)          # and the zero-copy path on the new range
+        sums = st.read_sums()[0]
+        assert np.array_equal(oracle_mod.finish(sums).view(np.uint32), want[7 * first:7 * (first + n)].view(np.uint32))
+        st.reset()
+    with pytest.raises(b2p.B2pError):
+        st.set_chunk_range(40, 9)                      # past the end of the frame
+    st.close()
+    fixed = b2p.Baseband2Power(kernel=kernel, nchunk=6, first_chunk=0, nchunk_total=48)
+    with pytest.raises(b2p.B2pError):
+        fixed.set_chunk_range(6, 6)                    # not created resizable
+    fixed.close()
+    pin.free()
