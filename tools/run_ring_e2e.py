@@ -75,9 +75,12 @@ def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300,
     except Exception:
         pass
     groups = re.findall(r"gpu (\d+): host link ([0-9.]+) GB/s -> (\d+) chunks", log)
+    moves = re.findall(r"rebalanced chunks per gpu:((?: gpu\d+:\d+)+)", log)
+    final = [int(x.split(":")[1]) for x in moves[-1].split()] if moves else None
     return {"path": "paf_memdb -> ring -> paf_baseband2power -> ring -> paf_dbdisk",
             "gpu": gpu, "keys": [kin, kout], "_spectra": spectra,
             "channel_groups": [{"gpu": int(a), "link_GBps": float(b), "chunks": int(c)} for a, b, c in groups] or None,
+            "rebalanced": len(moves), "chunks_after_rebalancing": final,
             "ndf_per_block": ndf, "ring_blocks": nbufs, "blocks": nin, "spectra": nout,
             "spectra_file_bytes": size, "ring_pinned": "ring pinned" in log,
             "stage_busy_s": busy, "stage_GBps": round(nin * blk / busy / 1e9, 3),
