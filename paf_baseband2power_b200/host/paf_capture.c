@@ -31,7 +31,10 @@
  *                        opens (the role of the reference's tbuf, sync.c:150-165).
  *
  * Extra flags: -I bind address, -p first port, -n ports, -t socket timeout [s],
- * -w spill window in frames (stock back-end), -G 0 switches UDP_GRO off.
+ * -w spill window in frames (stock back-end), -G 0 switches UDP_GRO off, -x the longest
+ * time [ms] a port that has run past the window waits for the other ports before the oldest
+ * block is retired (the port threads are not in step; without the wait a fast port would turn
+ * the slower ports' frames into late ones).
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -98,9 +101,12 @@ typedef struct capture_t {
   int64_t base; /* index of blk[0] */
   int header_done;
   /* statistics */
-  atomic_ullong n_recv, n_late, n_early, n_invalid, n_missing, n_blocks, n_msgs, ns_blocked;
+  atomic_ullong n_recv, n_late, n_early, n_invalid, n_missing, n_blocks, n_msgs, ns_blocked, ns_held;
   atomic_ullong port_recv[16];
   volatile int port_done[16]; /* the port has seen a frame past the requested length */
+  atomic_llong port_block[16]; /* newest block a frame of this port belonged to */
+  atomic_int port_silent[16];  /* the port let a retirement wait run out: not waited for again until it speaks */
+  int64_t lag_wait_ns;         /* longest a port that is ahead holds back for the others */
   atomic_int quit, ndone;
 } capture_t;
 
@@ -129,7 +135,8 @@ static void usage(void)
           " -k Directory for the log file \n"
           " -h Show help \n"
           "extensions: -I bind address  -p first port [17100]  -n ports [6]  -t socket timeout s [27]\n"
-          "            -w spill window in frames (stock PSRDADA back-end) [256]  -G 0 no UDP_GRO\n");
+          "            -w spill window in frames (stock PSRDADA back-end) [256]  -G 0 no UDP_GRO\n"
+          "            -x longest wait [ms] of a port that is a block ahead for the others [200]\n");
 }
 
 /* UTC_START / PICOSECONDS of the reference frame: capture.c:791-843 (acquire_start_time) */
@@ -319,6 +326,14 @@ typedef struct port_arg_t {
   int iport;
 } port_arg_t;
 
+/* a port other than `self` that still delivers into the oldest open block, or -1 */
+static int laggard(const capture_t *c, int self)
+{
+  for (int k = 0; k < c->nports; ++k)
+    if (k != self && !c->port_done[k] && !atomic_load(&c->port_silent[k]) && atomic_load(&c->port_block[k]) <= c->base) return k;
+  return -1;
+}
+
 /* one BMF frame (header + payload) from source address `from` into the window; the caller
    holds the read lock and gets it back */
 static void place_frame(capture_t *c, int iport, const unsigned char *frame, const struct sockaddr_in *from)
@@ -357,9 +372,28 @@ static void place_frame(capture_t *c, int iport, const unsigned char *frame, con
   }
   const int64_t bi = f / (int64_t)c->ndf_block;
   const uint64_t fin = (uint64_t)(f % (int64_t)c->ndf_block);
+  if (bi > atomic_load(&c->port_block[iport])) atomic_store(&c->port_block[iport], bi);
+  atomic_store(&c->port_silent[iport], 0);
   /* beyond the window (two blocks ahead, or past the spill window of the next block):
-     retire the oldest block */
+     retire the oldest block — once the other ports are through with it.  The port threads do
+     not run in step; one that is ahead holds back here (its packets queue in the socket
+     buffer) for at most lag_wait_ns instead of turning the others' frames into late ones. */
+  uint64_t waited = 0;
   while ((bi > c->base + 1 || (bi == c->base + 1 && fin >= c->ahead_ndf)) && !atomic_load(&c->quit)) {
+    const int lag = laggard(c, iport);
+    if (lag >= 0 && waited < (uint64_t)c->lag_wait_ns) {
+      const uint64_t t0 = now_ns();
+      pthread_rwlock_unlock(&c->win);
+      usleep(50);
+      pthread_rwlock_rdlock(&c->win);
+      const uint64_t dt = now_ns() - t0;
+      waited += dt;
+      atomic_fetch_add(&c->ns_held, dt);
+      continue;
+    }
+    if (lag >= 0) /* the wait ran out: do not wait for these again until they deliver */
+      for (int k = 0; k < c->nports; ++k)
+        if (k != iport && !c->port_done[k] && atomic_load(&c->port_block[k]) <= c->base) atomic_store(&c->port_silent[k], 1);
     pthread_rwlock_unlock(&c->win);
     pthread_rwlock_wrlock(&c->win);
     if (bi > c->base + 1 || (bi == c->base + 1 && fin >= c->ahead_ndf)) rotate(c, 1);
@@ -502,9 +536,10 @@ int main(int argc, char **argv)
   c->timeout_s = BMF_PRD_SEC;
   c->want_gro = 1;
   c->ahead_ndf = 256;
+  c->lag_wait_ns = 200 * 1000000ll;
   strcpy(c->dir, ".");
   int arg;
-  while ((arg = getopt(argc, argv, "a:b:c:d:e:f:g:hi:j:k:I:p:n:t:w:G:")) != -1) {
+  while ((arg = getopt(argc, argv, "a:b:c:d:e:f:g:hi:j:k:I:p:n:t:w:G:x:")) != -1) {
     switch (arg) {
       case 'h': usage(); return EXIT_FAILURE;
       case 'a':
@@ -528,6 +563,7 @@ int main(int argc, char **argv)
       case 't': c->timeout_s = atoi(optarg); break;
       case 'w': c->ahead_ndf = strtoull(optarg, NULL, 10); break;
       case 'G': c->want_gro = atoi(optarg) != 0; break;
+      case 'x': c->lag_wait_ns = (int64_t)(atof(optarg) * 1e6); break;
       default: usage(); return EXIT_FAILURE;
     }
   }
@@ -632,10 +668,10 @@ int main(int argc, char **argv)
            (unsigned long long)atomic_load(&c->n_missing), (unsigned long long)atomic_load(&c->n_late),
            (unsigned long long)atomic_load(&c->n_early), (unsigned long long)atomic_load(&c->n_invalid),
            (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
-  multilog(runtime_log, LOG_INFO, "udp_gro %s  messages %llu (%.2f frames per message)  blocked on a full ring %.3f s\n",
+  multilog(runtime_log, LOG_INFO, "udp_gro %s  messages %llu (%.2f frames per message)  blocked on a full ring %.3f s  held for slower ports %.3f s\n",
            c->gro_on ? "on" : "off", (unsigned long long)atomic_load(&c->n_msgs),
            (double)atomic_load(&c->n_recv) / (double)(atomic_load(&c->n_msgs) ? atomic_load(&c->n_msgs) : 1),
-           1e-9 * (double)atomic_load(&c->ns_blocked));
+           1e-9 * (double)atomic_load(&c->ns_blocked), 1e-9 * (double)atomic_load(&c->ns_held));
   for (int i = 0; i < c->nports; ++i)
     multilog(runtime_log, LOG_INFO, "port %d: %llu frames\n", c->port_base + i, (unsigned long long)atomic_load(&c->port_recv[i]));
 
