@@ -67,6 +67,9 @@ typedef struct conf_t {
   /* statistics */
   uint64_t nblocks_in, nblocks_out, nframes_dropped;
   double seconds_busy;
+  /* the same for the blocks after the split has settled (group mode tunes on the first 8) */
+  uint64_t nblocks_steady;
+  double seconds_busy_steady, seconds_block_max;
 } conf_t;
 
 void default_baseband2power(conf_t *conf);

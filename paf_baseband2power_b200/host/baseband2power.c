@@ -297,7 +297,13 @@ int do_baseband2power(conf_t *conf)
         multilog(conf->log, LOG_INFO, "rebalanced chunks per gpu:%s\n", txt);
       }
     }
-    conf->seconds_busy += now_s() - t0;
+    const double dt = now_s() - t0;
+    conf->seconds_busy += dt;
+    if (!tuning) {
+      conf->nblocks_steady++;
+      conf->seconds_busy_steady += dt;
+      if (dt > conf->seconds_block_max) conf->seconds_block_max = dt;
+    }
   }
   if (due && collect_spectra(conf, &due, due) != EXIT_SUCCESS) return EXIT_FAILURE;
   if (in_integration) { /* an incomplete integration has the wrong scale: do not emit it */
@@ -313,6 +319,9 @@ int do_baseband2power(conf_t *conf)
   if (conf->log)
     multilog(conf->log, LOG_INFO, "END: %lu blocks in, %lu spectra out, %.3f s busy\n",
              (unsigned long)conf->nblocks_in, (unsigned long)conf->nblocks_out, conf->seconds_busy);
+  if (conf->log && conf->nblocks_steady)
+    multilog(conf->log, LOG_INFO, "STEADY: %lu blocks after the split settled, %.3f s busy, slowest block %.4f s\n",
+             (unsigned long)conf->nblocks_steady, conf->seconds_busy_steady, conf->seconds_block_max);
   return EXIT_SUCCESS;
 }
 

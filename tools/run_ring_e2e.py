@@ -65,6 +65,11 @@ def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300,
     log = open(os.path.join(d, "paf_baseband2power.log")).read()
     m = re.search(r"END: (\d+) blocks in, (\d+) spectra out, ([0-9.]+) s busy", log)
     nin, nout, busy = int(m.group(1)), int(m.group(2)), float(m.group(3))
+    st = re.search(r"STEADY: (\d+) blocks after the split settled, ([0-9.]+) s busy, slowest block ([0-9.]+) s", log)
+    steady = None
+    if st and float(st.group(2)) > 0:
+        steady = {"blocks": int(st.group(1)), "busy_s": float(st.group(2)), "slowest_block_s": float(st.group(3)),
+                  "GBps": round(int(st.group(1)) * blk / float(st.group(2)) / 1e9, 3)}
     gen = re.search(r"published .* in ([0-9.]+) s", prod.stderr)
     size = os.path.getsize(os.path.join(d, "spectra.dada"))
     t_int = ndf * 128 * 27.0 / 32.0 * 1e-6
@@ -84,7 +89,7 @@ def run(ndf=8192, nbufs=4, nblocks=16, gpu=0, kernel="auto", pin=1, timeout=300,
             "ndf_per_block": ndf, "ring_blocks": nbufs, "blocks": nin, "spectra": nout,
             "spectra_file_bytes": size, "ring_pinned": "ring pinned" in log,
             "stage_busy_s": busy, "stage_GBps": round(nin * blk / busy / 1e9, 3),
-            "stage_realtime_factor": round(nin * t_int / busy, 2),
+            "stage_realtime_factor": round(nin * t_int / busy, 2), "steady": steady,
             "wall_s": round(wall, 3), "producer_s": float(gen.group(1)) if gen else None}
 
 
