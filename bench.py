@@ -629,9 +629,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs: copy, read+write)",
                 "traffic": (tr or {}).get("dram_bytes_per_launch"),
-                "traffic_source": ((tr or {}).get("source", "profiles/roofline_traffic.json")
-                                   + " (ncu --set full capture of this kernel, not this run)") if tr else None,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel": f"b2p_fused_{st.kernel}_bmf",
+                "traffic_source": ("ncu, not this run: " + (tr or {}).get("source", "profiles/roofline_traffic.json")) if tr else None,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel": {"ldg": "b2p_fused_ldg256_bmf", "tma": "b2p_fused_tma_bmf"}.get(st.kernel, st.kernel),
                 "launch_ms": round(per_launch_ms, 5), "launches_timed": fused_n,
                 "timing": "isolated per-launch CUDA events on the launching stream, second pass of K steps "
                           "(the launch includes the cross-CTA reduce and the float32 finish)",
