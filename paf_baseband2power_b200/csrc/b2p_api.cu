@@ -169,17 +169,20 @@ static int resolve_nsplit(const b2p_params *p, int kernel, int sm_count, int *ba
 {
   *base_out = 0;
   if (p->nsplit > 0) return p->nsplit > 1024 ? 1024 : p->nsplit;
-  /* base = smallest split count that makes the grid a whole number of waves;
-     LDG: 4 CTAs/SM and ~37 frames per CTA measured best (18 waves for one beam). */
+  /* base = smallest split count that makes the grid a whole number of waves.  With the
+     cross-CTA fold inside the kernel every CTA costs a prologue, a block reduction and an
+     arrival, so fewer, longer CTAs win: 74 splits (6 waves of 4 CTAs/SM for one beam, ~110
+     frames per CTA) beat round 1's 222 by 0.8 % chained and 0.9 % isolated; 37 and 111 are
+     within 0.3 % of 74, 444 is 4 % behind (profiles/r02_nsplit_sweep.txt). */
   unsigned slots, units, target;
   if (kernel == B2P_KERNEL_TMA) {
     slots = (unsigned)sm_count;
     units = (unsigned)(p->nchunk / b2p_tma_group(p->nchunk)) * (unsigned)p->nbeam;
-    target = 222; /* items are drawn dynamically: many small ones balance the SMs */
+    target = 74; /* items are drawn dynamically; 74: +3.4 % chained, +2.6 % isolated over 222 */
   } else {
     slots = 4u * (unsigned)sm_count;
     units = (unsigned)p->nchunk * (unsigned)p->nbeam;
-    target = 222; /* 8192 frames / 222 = 37 frames per CTA */
+    target = 74; /* 8192 frames / 74 = 110 frames per CTA (tapered 131 / 65 / 33) */
   }
   const unsigned base = slots / gcd_u(slots, units); /* smallest n with n*units % slots == 0 */
   *base_out = (int)(base > 1024 ? 1024 : base);
