@@ -103,7 +103,7 @@ typedef struct capture_t {
   /* statistics */
   atomic_ullong n_recv, n_late, n_early, n_invalid, n_missing, n_blocks, n_msgs, ns_blocked, ns_held;
   atomic_ullong port_recv[16];
-  volatile int port_done[16]; /* the port has seen a frame past the requested length */
+  atomic_int port_done[16];    /* the port has seen a frame past the requested length */
   atomic_llong port_block[16]; /* newest block a frame of this port belonged to */
   atomic_int port_silent[16];  /* the port let a retirement wait run out: not waited for again until it speaks */
   int64_t lag_wait_ns;         /* longest a port that is ahead holds back for the others */
