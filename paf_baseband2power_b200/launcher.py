@@ -13,6 +13,9 @@ Same flags (-a conf, -b directory, -c gpu, -d visible gpu, -e memcheck) plus the
 data-file name the reference forgot to declare (-f).  Multi-beam: --beams N runs
 N independent pipelines (own ring keys per beam, beam b on GPU gpus[b % len]) —
 the sharding of DESIGN.md §7; no process talks to another beam's process.
+--gpus-per-beam K gives every beam K GPUs of the -c list: its stage then runs
+`paf_baseband2power -d g0,g1,...` and spreads the beam's chunks over them as channel
+groups (one ring pair, one stage process, every one of the K host links in use).
 """
 from __future__ import annotations
 
@@ -98,9 +101,12 @@ def _pin(cmd: List[str], cpu: int | None) -> List[str]:
 
 def plan(conf: PipelineConf, directory: str, dfnames: List[str], gpus: List[int], memcheck: bool = False,
          hfname: str | None = None, extra_stage_args: List[str] | None = None, pin: bool = True,
-         ngpus_box: int = 0) -> List[BeamPlan]:
+         ngpus_box: int = 0, gpus_per_beam: int = 1) -> List[BeamPlan]:
     """The exact commands for every beam; nothing is executed here.  `gpus` empty: beams are
-    spread over the `ngpus_box` GPUs of the box (sharding.gpu_for_rank)."""
+    spread over the `ngpus_box` GPUs of the box (sharding.gpu_for_rank).  `gpus_per_beam` K > 1:
+    beam b gets GPUs gpus[b*K : b*K+K] (wrapping around the list) as channel groups."""
+    if gpus_per_beam > 1 and len(gpus) < gpus_per_beam:
+        raise ValueError(f"--gpus-per-beam {gpus_per_beam} needs at least that many GPUs in -c")
     plans = []
     hf = hfname or conf.diskdb_hfname
     if not os.path.isabs(hf):
@@ -120,7 +126,11 @@ def plan(conf: PipelineConf, directory: str, dfnames: List[str], gpus: List[int]
         ]
         bp.destroy = [[db, "-d", "-k", f"{kin:x}"], [db, "-d", "-k", f"{kout:x}"]]
         cpu0 = 3 * beam if pin else None
-        stage = [os.path.join(BIN, "paf_baseband2power"), "-a", f"{kin:x}", "-b", f"{kout:x}", "-c", directory, "-d", str(gpu)]
+        dev = str(gpu)
+        if gpus_per_beam > 1:
+            mine = [gpus[(beam * gpus_per_beam + i) % len(gpus)] for i in range(gpus_per_beam)]
+            bp.gpu, dev = mine[0], ",".join(str(x) for x in mine)
+        stage = [os.path.join(BIN, "paf_baseband2power"), "-a", f"{kin:x}", "-b", f"{kout:x}", "-c", directory, "-d", dev]
         stage += extra_stage_args or []
         if memcheck:  # the reference wrapped the stage in cuda-memcheck (:89-90); its successor:
             stage = ["compute-sanitizer", "--tool", "memcheck"] + stage
@@ -211,6 +221,9 @@ def main(argv=None) -> int:
     ap.add_argument("--spread", type=int, default=0, metavar="NGPU",
                     help="ignore -c and spread the beams over the box's NGPU GPUs (beam i -> GPU floor(i*NGPU/nbeams)): "
                          "neighbouring GPUs tend to share a host bridge, and this path is bound by the host links")
+    ap.add_argument("--gpus-per-beam", type=int, default=1, metavar="K",
+                    help="give every beam K GPUs of the -c list: its stage spreads the beam's chunks over them as "
+                         "channel groups (paf_baseband2power -d g0,g1,...), so one beam uses K host links")
     ap.add_argument("--dry-run", action="store_true", help="print the commands, run nothing")
     ap.add_argument("--timeout", type=float, default=None)
     args = ap.parse_args(argv)
@@ -224,7 +237,7 @@ def main(argv=None) -> int:
         os.environ["CUDA_VISIBLE_DEVICES"] = args.visiblegpu
     extra = ["-s", "1"] if args.average else []
     plans = plan(conf, args.directory, args.dfname, [] if args.spread else args.gpu, bool(args.memcheck),
-                 extra_stage_args=extra, ngpus_box=args.spread)
+                 extra_stage_args=extra, ngpus_box=args.spread, gpus_per_beam=args.gpus_per_beam)
     if args.dry_run:
         for bp in plans:
             for cmd in bp.create + bp.stages + bp.destroy:
