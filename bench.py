@@ -505,6 +505,16 @@ def main():
         host_barrier()
         h2d_link = b2p_api.probe_h2d([gpu], nbytes=1 << 30, reps=3)[0]
         links = all_gather_floats(h2d_link)
+        links_equal_bytes = None
+        if world > 1:
+            # Equal byte counts let the fast links finish first and the slow ones then run alone,
+            # which reads too high.  Second pass: bytes in proportion to the first pass's rates, so
+            # every link stays loaded to the end — what the links deliver TOGETHER.
+            links_equal_bytes = links
+            nb2 = max(1 << 20, int((1 << 30) * h2d_link / max(links)) & ~255)
+            host_barrier()
+            h2d_link = b2p_api.probe_h2d([gpu], nbytes=nb2, reps=3)[0]
+            links = all_gather_floats(h2d_link)
         barrier()
         t0 = time.perf_counter()
         for i in range(ke):
@@ -522,6 +532,9 @@ def main():
                "h2d_link_GBps_per_gpu": round(h2d_link, 2),
                "h2d_link_GBps_all_ranks": [round(x, 2) for x in links],
                "h2d_links_sum_GBps": round(sum(links), 2),
+               "h2d_link_probe": ("all ranks copy at once, bytes per rank in proportion to a first pass's rates so that "
+                                  "every link stays loaded to the end" if world > 1 else "3 x 1 GiB pinned cudaMemcpyAsync"),
+               "h2d_link_GBps_equal_bytes_pass": [round(x, 2) for x in links_equal_bytes] if links_equal_bytes else None,
                "frac_of_h2d_link": round(nbeam * blk / (e2e_ms * 1e-3) / 1e9 / h2d_link, 4),
                "frac_of_h2d_links_sum": round(by_beam / sum(links), 4),
                "path": "b2p_integrate_host (pinned ring block, 256-frame pieces, 3 staging buffers, one launch per piece, spectrum D2H)"

@@ -236,15 +236,18 @@ int  b2p_group_wait_output(b2p_group *g, float *out_host);
 int  b2p_group_reset(b2p_group *g);
 /* Between integrations: move chunks towards the GPUs whose links delivered more during the
    last host call (H2D time per shard, CUDA events), half way per call.  *changed = 1 when the
-   split moved (the shard contexts are then rebuilt). */
+   split moved (the shard contexts are resizable: the ranges move in place, nothing is rebuilt). */
 int  b2p_group_rebalance(b2p_group *g, int *changed);
 int  b2p_group_size(const b2p_group *g);                  /* shards with >= 1 chunk */
 b2p_ctx *b2p_group_ctx(const b2p_group *g, int i);
 int  b2p_group_shard(const b2p_group *g, int i, int *device, int *first_chunk, int *nchunk);
 const char *b2p_group_last_error(const b2p_group *g);
 
-/* Pinned host -> device copy rate of each listed GPU with all of them copying at once
-   (`reps` copies of `bytes` each): the link weights for b2p_split_chunks. */
+/* Pinned host -> device copy rate of each listed GPU with all of them copying at once: the
+   link weights for b2p_split_chunks.  Two passes of `reps` copies: the first moves `bytes` per
+   copy over every link, the second bytes in proportion to the first pass's rates, so that all
+   links stay loaded to the end — what is returned is what they deliver TOGETHER (equal byte
+   counts let the slow links finish alone and read too high). */
 int b2p_probe_h2d(const int *devices, int n, size_t bytes, int reps, double *gbps_out);
 /* Split nchunk chunks over n parts in proportion to weights (NULL = equal), largest
    remainder; counts[] sums to nchunk exactly. */

@@ -846,26 +846,41 @@ int b2p_probe_h2d(const int *devices, int n, size_t bytes, int reps, double *gbp
     cudaSetDevice(devices[i]);
     e = cudaStreamSynchronize(st[i]);
   }
-  /* all links at once: every device's copies are queued before any is waited for */
-  for (int i = 0; i < n && e == cudaSuccess; ++i) {
-    cudaSetDevice(devices[i]);
-    e = cudaEventRecord(e0[i], st[i]);
-  }
-  for (int r = 0; r < reps && e == cudaSuccess; ++r)
+  /* all links at once: every device's copies are queued before any is waited for.  Pass 1
+     moves the same bytes over every link, so the fast links finish first and the slow ones
+     then run with less company — their rate reads too high.  Pass 2 hands every link bytes in
+     proportion to its pass-1 rate, so that all stay busy until the end: its rates are what the
+     links deliver TOGETHER, which is what a split over them needs. */
+  size_t nbytes[B2P_MAX_GROUP];
+  for (int i = 0; i < n; ++i) nbytes[i] = bytes;
+  for (int pass = 0; pass < (n > 1 ? 2 : 1) && e == cudaSuccess; ++pass) {
     for (int i = 0; i < n && e == cudaSuccess; ++i) {
       cudaSetDevice(devices[i]);
-      e = cudaMemcpyAsync(dev[i], host, bytes, cudaMemcpyHostToDevice, st[i]);
+      e = cudaEventRecord(e0[i], st[i]);
     }
-  for (int i = 0; i < n && e == cudaSuccess; ++i) {
-    cudaSetDevice(devices[i]);
-    e = cudaEventRecord(e1[i], st[i]);
-  }
-  for (int i = 0; i < n && e == cudaSuccess; ++i) {
-    cudaSetDevice(devices[i]);
-    float ms = 0.f;
-    if ((e = cudaEventSynchronize(e1[i])) != cudaSuccess) break;
-    if ((e = cudaEventElapsedTime(&ms, e0[i], e1[i])) != cudaSuccess) break;
-    gbps_out[i] = ms > 0.f ? (double)reps * (double)bytes / (ms * 1e-3) / 1e9 : 0.0;
+    for (int r = 0; r < reps && e == cudaSuccess; ++r)
+      for (int i = 0; i < n && e == cudaSuccess; ++i) {
+        cudaSetDevice(devices[i]);
+        e = cudaMemcpyAsync(dev[i], host, nbytes[i], cudaMemcpyHostToDevice, st[i]);
+      }
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+      cudaSetDevice(devices[i]);
+      e = cudaEventRecord(e1[i], st[i]);
+    }
+    double best = 0.0;
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+      cudaSetDevice(devices[i]);
+      float ms = 0.f;
+      if ((e = cudaEventSynchronize(e1[i])) != cudaSuccess) break;
+      if ((e = cudaEventElapsedTime(&ms, e0[i], e1[i])) != cudaSuccess) break;
+      gbps_out[i] = ms > 0.f ? (double)reps * (double)nbytes[i] / (ms * 1e-3) / 1e9 : 0.0;
+      if (gbps_out[i] > best) best = gbps_out[i];
+    }
+    for (int i = 0; i < n && best > 0.0; ++i) {
+      size_t b = (size_t)((double)bytes * gbps_out[i] / best);
+      b &= ~(size_t)255;
+      nbytes[i] = b < 4096 ? (bytes < 4096 ? bytes : 4096) : b;
+    }
   }
   for (int i = 0; i < n; ++i) {
     if (devices[i] >= 0) cudaSetDevice(devices[i]);

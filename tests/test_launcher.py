@@ -120,23 +120,3 @@ def test_gpus_per_beam_plan_gives_the_stage_a_gpu_list(tmp_path):
     with pytest.raises(ValueError):
         launcher.plan(c, str(tmp_path), ["a.dada"], [0], pin=False, gpus_per_beam=2)
 
-
-@pytest.mark.gpu
-def test_one_beam_over_a_gpu_list_through_the_launcher(tmp_path, oracle_mod, b2p):
-    """The launcher's --gpus-per-beam: one beam, its chunks over two GPUs (the same GPU twice on a
-    one-GPU box: two shard contexts), spectra bit-identical to the oracle."""
-    ndf_block, nblk = 32, 3
-    hdr = os.path.join(PKG, "conf", "header_baseband2power.txt")
-    subprocess.run([os.path.join(BIN, "b2p_gen"), "-o", str(tmp_path / "beam.dada"), "-n", str(ndf_block * nblk),
-                    "-s", "71", "-H", hdr], check=True, capture_output=True)
-    gpus = ["0", "1"] if b2p.device_count() >= 2 else ["0", "0"]
-    rc = launcher.main(["-a", CONF, "-b", str(tmp_path), "-c", *gpus, "-d", "", "-e", "0", "-f", "beam.dada",
-                        "--ndf", str(ndf_block), "--nblk", "3", "--gpus-per-beam", "2", "--timeout", "120"])
-    assert rc == 0
-    out = (tmp_path / "beam00_spectra.dada").read_bytes()
-    spectra = np.frombuffer(out[4096:], dtype=np.float32).reshape(nblk, 336)
-    payload = np.fromfile(tmp_path / "beam.dada", dtype=np.uint8)[4096:]
-    per = ndf_block * 48 * 7168
-    for i in range(nblk):
-        want = oracle_mod.finish(oracle_mod.accumulate_omp(payload[i * per:(i + 1) * per]))
-        assert np.array_equal(spectra[i].view(np.uint32), want.view(np.uint32)), i
