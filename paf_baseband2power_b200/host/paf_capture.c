@@ -373,7 +373,7 @@ static void place_frame(capture_t *c, int iport, const unsigned char *frame, con
   const int64_t bi = f / (int64_t)c->ndf_block;
   const uint64_t fin = (uint64_t)(f % (int64_t)c->ndf_block);
   if (bi > atomic_load(&c->port_block[iport])) atomic_store(&c->port_block[iport], bi);
-  atomic_store(&c->port_silent[iport], 0);
+  if (atomic_load(&c->port_silent[iport])) atomic_store(&c->port_silent[iport], 0); /* read-mostly: no line ping-pong between the ports */
   /* beyond the window (two blocks ahead, or past the spill window of the next block):
      retire the oldest block — once the other ports are through with it.  The port threads do
      not run in step; one that is ahead holds back here (its packets queue in the socket
